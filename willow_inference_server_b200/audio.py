@@ -1,0 +1,136 @@
+"""Drop-in for ``wis/audio.py`` (the names ``main.py:52-57`` imports), running on the B200.
+
+    from willow_inference_server_b200.audio import (
+        log_mel_spectrogram, pad_or_trim, chunk_iter, find_longest_common_sequence)
+
+* ``log_mel_spectrogram`` replaces /root/reference/wis/audio.py:72-103: same argument (float32 numpy PCM), returns an
+  object with ``.numpy()`` -> float32 [80, n_frames] exactly as the call sites use it (main.py:608,614).  The STFT /
+  mel / log pipeline runs in the CUDA kernel csrc/logmel.cu; there is no CPU path.
+* ``pad_or_trim`` (wis/audio.py:28-51) is kept for API compatibility; the kernel fuses padding/trimming, so calling
+  it first is allowed but not required (``log_mel_spectrogram`` accepts the unpadded utterance too).
+* ``chunk_iter`` / ``find_longest_common_sequence`` (wis/audio.py:106-159) are host logic on token lists and are
+  restated here with the same behaviour (goldens: tests/golden/host_logic.json).
+"""
+from __future__ import annotations
+
+import os
+import threading
+
+import numpy as np
+
+from . import _lib
+
+SAMPLE_RATE = 16000
+N_FFT = 400
+N_MELS = 80
+HOP_LENGTH = 160
+CHUNK_LENGTH = 30
+N_SAMPLES = CHUNK_LENGTH * SAMPLE_RATE
+N_FRAMES = N_SAMPLES // HOP_LENGTH
+
+chunk_length_s = 22
+stride_length_s = [4, 4]
+chunk_len = chunk_length_s * SAMPLE_RATE
+stride_left = stride_length_s[0] * SAMPLE_RATE
+stride_right = stride_length_s[1] * SAMPLE_RATE
+
+_frontend = None
+_frontend_lock = threading.Lock()
+
+
+def _get_frontend() -> "_lib.Handle":
+    global _frontend
+    with _frontend_lock:
+        if _frontend is None:
+            _frontend = _lib.Handle.frontend(int(os.environ.get("WISB_DEVICE", "0")))
+        return _frontend
+
+
+class MelFeatures:
+    """What the reference gets back from torch: something with ``.numpy()`` and a shape."""
+
+    def __init__(self, arr: np.ndarray):
+        self._a = arr
+
+    def numpy(self) -> np.ndarray:
+        return self._a
+
+    @property
+    def shape(self):
+        return self._a.shape
+
+    def __array__(self, dtype=None, copy=None):
+        return self._a if dtype is None else self._a.astype(dtype)
+
+
+def pad_or_trim(array, length: int = N_SAMPLES, *, axis: int = -1):
+    array = np.asarray(array)
+    n = array.shape[axis]
+    if n > length:
+        array = np.take(array, np.arange(length), axis=axis)
+    elif n < length:
+        widths = [(0, 0)] * array.ndim
+        widths[axis] = (0, length - n)
+        array = np.pad(array, widths)
+    return array
+
+
+def log_mel_spectrogram(audio, n_mels: int = N_MELS) -> MelFeatures:
+    if n_mels != N_MELS:
+        raise AssertionError(f"Unsupported n_mels: {n_mels}")
+    if isinstance(audio, str):
+        raise TypeError("log_mel_spectrogram takes PCM samples (numpy), not a path")
+    pcm = np.asarray(audio)
+    if pcm.dtype not in (np.float32, np.int16):
+        pcm = pcm.astype(np.float32)
+    if pcm.ndim != 1:
+        raise ValueError("audio must be a 1-D array of 16 kHz samples")
+    mel = _get_frontend().logmel(pcm, [0], [pcm.shape[0]])
+    return MelFeatures(mel[0])
+
+
+def log_mel_batch(pcm_list, handle=None) -> np.ndarray:
+    """Batched form used by the engine-side tests/bench: list of 1-D arrays -> float32 [B, 80, 3000]."""
+    h = handle or _get_frontend()
+    dt = np.int16 if all(np.asarray(p).dtype == np.int16 for p in pcm_list) else np.float32
+    arrs = [np.ascontiguousarray(p, dt) for p in pcm_list]
+    n = np.array([a.shape[0] for a in arrs], np.int32)
+    off = np.zeros(len(arrs), np.int64)
+    off[1:] = np.cumsum(n[:-1])
+    flat = np.concatenate(arrs) if arrs else np.zeros(0, dt)
+    return h.logmel(flat, off, n)
+
+
+def chunk_iter(inputs):
+    """30-s windows (22 s payload + 4 s context each side, 14 s step) -- wis/audio.py:106-134."""
+    if not isinstance(inputs, np.ndarray):
+        raise AssertionError("chunk_iter only takes numpy array")
+    total = inputs.shape[0]
+    step = chunk_len - stride_left - stride_right
+    for start in range(0, total, step):
+        piece = inputs[start : start + chunk_len]
+        left = 0 if start == 0 else stride_left
+        last = start + step + stride_left >= total
+        right = 0 if last else stride_right
+        if piece.shape[0] > left:
+            yield piece, (piece.shape[0], left, right)
+
+
+def find_longest_common_sequence(sequences, tokenizer):
+    """Token-level stitch of overlapping windows -- wis/audio.py:139-159 (same scoring: fraction of matches + i/10000,
+    at least two matches).  Unlike the reference this does not raise when a later window is longer than the text
+    accumulated so far (numpy broadcasting error there): the comparison is limited to the overlap."""
+    special = set(tokenizer.all_special_ids)
+    merged = [t for t in sequences[0][0] if t not in special]
+    for item in sequences[1:]:
+        new = [t for t in item[0] if t not in special]
+        best_i, best = 0, 0.0
+        for i in range(1, len(new) + 1):
+            tail, head = merged[-i:], new[:i]
+            # (the reference compares numpy arrays here and raises once i exceeds len(merged))
+            matches = sum(1 for a, b in zip(tail, head) if a == b) if len(tail) == len(head) else 0
+            score = matches / i + i / 10000.0
+            if matches > 1 and score > best:
+                best_i, best = i, score
+        merged.extend(new[best_i:])
+    return np.array(merged)

@@ -1,0 +1,96 @@
+// Decoder-side kernel interface (decoder.cu / search.cu).  Token loop of ctranslate2.models.Whisper.generate
+// (/root/reference/main.py:687-692).
+#pragma once
+#include "common.cuh"
+
+namespace wisb {
+
+constexpr int DEC_MAX_ROWS = 16;   // rows (utterances x beams) one decoder pass handles
+constexpr int MAX_BEAM = 8;
+constexpr int MAX_CAND = 2 * MAX_BEAM;
+constexpr int TOPK_CHUNKS = 32;
+
+// Everything the captured decode graphs read at run time lives in device memory so one graph serves every step.
+struct DecState {
+  int pos;        // position of the token being fed this step
+  int gen_step;   // 0-based index of the token being generated (valid once pos >= prompt_len - 1)
+  int n_done;     // utterances finished
+  int all_done;   // n_done == n_utt
+};
+
+enum GemvEpi : int {
+  GV_STORE = 0,   // out[r, n] = v
+  GV_RESID = 1,   // out[r, n] += v
+  GV_GELU = 2,    // out[r, n] = gelu(v)
+  GV_QKV = 3,     // n < d: q[r, n] = v ; d <= n < 2d: kcache[slot r][pos][n - d] ; else vcache
+};
+
+struct GemvArgs {
+  const float* x = nullptr;   // [R, K] fp32
+  const float* ln_g = nullptr;  // LayerNorm prologue when non-null
+  const float* ln_b = nullptr;
+  const __half* w = nullptr;  // [N, K] fp16
+  const float* bias = nullptr;
+  float* out = nullptr;       // fp32 [R, ldo]
+  long long ldo = 0;
+  int R = 0, N = 0, K = 0;
+  int epi = GV_STORE;
+  // GV_QKV
+  __half* kcache = nullptr;   // [R_slots][t_max][d]
+  __half* vcache = nullptr;
+  int d_model = 0, t_max = 0;
+  const DecState* st = nullptr;
+};
+void gemv_run(const GemvArgs& a, cudaStream_t stream);
+
+// x[r, :] = tok_emb[token[r], :] + pos_emb[pos, :]
+void dec_embed_run(const int* tokens, const __half* tok_emb, const float* pos_emb, float* x, int R, int d,
+                   const DecState* st, cudaStream_t stream);
+
+// causal self-attention over the cache, with beam indirection: position t of row r lives in slot indir[r][t]
+// (two ping-pong indirection tables; *flip says which one is current)
+void dec_self_attn_run(const float* q /*[R,d]*/, const __half* kcache, const __half* vcache, const int* indir0,
+                       const int* indir1, const int* flip, float* ctx /*[R,d]*/, int R, int d, int H, int t_max,
+                       const DecState* st, cudaStream_t stream);
+
+// cross-attention: rows of utterance u share K/V [H][1536][64]; grid = (H, n_utt) x cluster of 8 CTAs over the keys
+void dec_cross_attn_run(const float* q /*[R,d]*/, const __half* k /*[n_utt_total][H][1536][64]*/, const __half* v,
+                        float* ctx, int n_utt, int beam, int d, int H, cudaStream_t stream);
+
+struct SearchArgs {
+  // inputs
+  const float* logits = nullptr;  // [R, ldl]
+  long long ldl = 0;
+  int n_vocab = 0;
+  const unsigned char* mask = nullptr;  // [V] bit0: suppressed always, bit1: suppressed at the first generated step
+  int n_utt = 0, beam = 0, n_cand = 0;
+  int max_new = 0, max_hyp = 0, eot = 0, t_max = 0, prompt_len = 0;
+  float length_penalty = 1.f;
+  // workspaces / state (device)
+  float* row_lse = nullptr;       // [R]
+  float* cum = nullptr;           // [R] cumulative log-prob of the alive beams
+  unsigned long long* part = nullptr;  // [R][TOPK_CHUNKS][MAX_CAND] packed (score, ~index)
+  float* cand_score = nullptr;    // [n_utt][MAX_CAND]
+  int* cand_idx = nullptr;        // [n_utt][MAX_CAND]   beam * V + token
+  int* tokens = nullptr;          // [R] token fed next step
+  int* seq[2] = {nullptr, nullptr};    // [R][max_new] generated tokens of the alive beams (ping-pong)
+  int* indir[2] = {nullptr, nullptr};  // [R][t_max] cache indirection (ping-pong)
+  int* flip = nullptr;            // which of the ping-pong buffers is current (device int)
+  int* done = nullptr;            // [n_utt]
+  int* n_hyp = nullptr;           // [n_utt]
+  float* best_score = nullptr;    // [n_utt]
+  int* best_len = nullptr;        // [n_utt]
+  int* best_tokens = nullptr;     // [n_utt][max_new]
+  DecState* st = nullptr;
+};
+void search_step_run(const SearchArgs& a, cudaStream_t stream);
+// prompt prefill: no search, just feed the next prompt token and advance the position
+void prefill_advance_run(int* tokens, const int* prompt /*[n_utt][prompt_len]*/, int prompt_len, int R, int beam,
+                         DecState* st, cudaStream_t stream);
+void search_init_run(const SearchArgs& a, const int* prompt, cudaStream_t stream);
+
+// language detection head: softmax over lang ids of the logits of row u*beam (one step on <|startoftranscript|>)
+void lang_probs_run(const float* logits, long long ldl, const int* lang_ids, int n_lang, int n_utt, int row_stride,
+                    float* probs /*[n_utt][n_lang]*/, cudaStream_t stream);
+
+}  // namespace wisb

@@ -1,0 +1,973 @@
+// libwisb200.so host side: handle, weight blob, workspaces, encoder / decoder orchestration and the C ABI
+// declared in include/wisb200.h.  Mirrors the call surface WIS uses on ctranslate2 (main.py:341-355, 638-640, 685-692).
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/wisb200.h"
+#include "decoder.cuh"
+#include "kernels.h"
+
+namespace wisb {
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct TensorRef {
+  const uint8_t* ptr = nullptr;
+  int dtype = 0, ndim = 0;
+  long long shape[4] = {1, 1, 1, 1};
+  long long numel() const { return shape[0] * shape[1] * shape[2] * shape[3]; }
+};
+
+struct Dims {
+  int d_model, n_heads, n_enc_layers, n_dec_layers, n_vocab, n_vocab_pad, n_text_ctx, n_mels, n_audio_ctx, sot, eot,
+      transcribe, translate, no_timestamps, sot_prev, sot_lm, no_speech, blank, lang_first, n_langs;
+};
+static_assert(sizeof(Dims) == WISB_N_DIMS * sizeof(int), "Dims must mirror the blob header");
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  void ensure(size_t count, bool zero = false) {
+    if (count <= n) return;
+    release();
+    WISB_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    n = count;
+    if (zero) WISB_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  void ensure(size_t count) {
+    if (count <= n) return;
+    if (p) cudaFreeHost(p);
+    WISB_CUDA(cudaMallocHost(&p, count * sizeof(T)));
+    n = count;
+  }
+  ~PinBuf() {
+    if (p) cudaFreeHost(p);
+  }
+};
+
+struct EncLayerPlans {
+  GemmPlan qkv, o, fc1, fc2;
+};
+
+struct DecLayerW {
+  const float *ln1g, *ln1b, *qkvb, *ob, *ln2g, *ln2b, *cqb, *cob, *ln3g, *ln3b, *fc1b, *fc2b;
+  const __half *qkvw, *ow, *cqw, *cow, *fc1w, *fc2w;
+};
+
+struct GraphKey {
+  int n_utt, beam, prompt_len, max_new, max_hyp, u0, b_total;
+  float lp;
+  bool operator<(const GraphKey& o) const {
+    return memcmp(this, &o, sizeof(GraphKey)) < 0;
+  }
+};
+struct DecGraphs {
+  cudaGraphExec_t prefill = nullptr, step = nullptr;
+};
+
+}  // namespace
+
+}  // namespace wisb
+
+using namespace wisb;
+
+struct wisb_handle {
+  int device = 0;
+  int num_sms = 148;
+  std::mutex mu;
+  cudaStream_t stream = nullptr;
+  Dims dims{};
+  // weights
+  uint8_t* blob = nullptr;
+  bool own_blob = false;
+  size_t blob_bytes = 0;
+  std::map<std::string, TensorRef> tensors;
+  std::vector<DecLayerW> dec_w;
+  // options
+  int use_graphs = 1, attn_v_mn = 1, attn_ref = 0, decode_poll = 1;
+  // front end
+  DevBuf<float> lm_tables;
+  DevBuf<unsigned> lm_max;
+  DevBuf<uint8_t> pcm_dev;
+  DevBuf<long long> pcm_off;
+  DevBuf<int> pcm_n;
+  DevBuf<float> mel;  // [B,80,3000]
+  int mel_B = 0;      // utterances currently held in `mel`
+  // encoder workspaces (capacity enc_cap utterances)
+  int enc_cap = 0;
+  DevBuf<__half> h1, xn, qkv, vt, ctx, hbuf, enc_out, ckv;
+  DevBuf<float> x;
+  GemmPlan plan_conv2, plan_ckv;
+  std::vector<EncLayerPlans> enc_plans;
+  AttnPlan attn_plan;
+  int plans_B = 0, plans_vmn = -1;
+  // decoder workspaces
+  DevBuf<float> dx, dq, dctx, dh, logits;
+  DevBuf<__half> kcache, vcache;  // [L][16][448][d]
+  DevBuf<uint8_t> mask_base, mask_cur;
+  std::vector<int> mask_extra;
+  DevBuf<float> row_lse, cum, cand_score, best_score, lang_probs;
+  DevBuf<unsigned long long> part;
+  DevBuf<int> cand_idx, tokens, seq0, seq1, ind0, ind1, flip, done, n_hyp, best_len, best_tokens, prompt_dev, lang_ids;
+  DevBuf<DecState> st;
+  PinBuf<int> pin_i;
+  PinBuf<float> pin_f;
+  PinBuf<uint8_t> pin_b;
+  std::map<GraphKey, DecGraphs> graphs;
+  // timing
+  cudaEvent_t ev[8] = {};
+  float timing[8] = {};
+  int launches = 0;
+
+  const TensorRef& T(const std::string& name) const {
+    auto it = tensors.find(name);
+    if (it == tensors.end()) throw Error(1, "weight blob is missing tensor '" + name + "'");
+    return it->second;
+  }
+  const __half* H(const std::string& n) const { return reinterpret_cast<const __half*>(T(n).ptr); }
+  const float* F(const std::string& n) const { return reinterpret_cast<const float*>(T(n).ptr); }
+};
+
+namespace {
+
+constexpr int T_MAX = 448;
+
+void parse_blob(wisb_handle* h, const std::vector<uint8_t>& head) {
+  WISB_REQUIRE(head.size() >= 256 && memcmp(head.data(), "WISB200\0", 8) == 0, "not a WISB200 weight blob");
+  uint32_t version, n_tensors;
+  memcpy(&version, head.data() + 8, 4);
+  memcpy(&n_tensors, head.data() + 12, 4);
+  WISB_REQUIRE(version == 1, "unsupported weight blob version");
+  memcpy(&h->dims, head.data() + 16, sizeof(Dims));
+  WISB_REQUIRE(head.size() >= 256 + 96ull * n_tensors, "truncated weight blob table");
+  for (uint32_t i = 0; i < n_tensors; ++i) {
+    const uint8_t* e = head.data() + 256 + 96ull * i;
+    char name[49] = {0};
+    memcpy(name, e, 48);
+    TensorRef t;
+    uint32_t dt, nd;
+    memcpy(&dt, e + 48, 4);
+    memcpy(&nd, e + 52, 4);
+    t.dtype = static_cast<int>(dt);
+    t.ndim = static_cast<int>(nd);
+    for (int k = 0; k < 4; ++k) {
+      int64_t s;
+      memcpy(&s, e + 56 + 8 * k, 8);
+      t.shape[k] = s;
+    }
+    uint64_t off;
+    memcpy(&off, e + 88, 8);
+    WISB_REQUIRE(off < h->blob_bytes, "tensor offset outside the blob");
+    t.ptr = h->blob + off;
+    h->tensors[name] = t;
+  }
+  const Dims& d = h->dims;
+  WISB_REQUIRE(d.d_model % 128 == 0 && d.d_model == 64 * d.n_heads && d.d_model <= 1536,
+               "engine requires head_dim 64 and d_model a multiple of 128 (<= 1536)");
+  WISB_REQUIRE(d.n_mels == N_MELS && d.n_audio_ctx == T_ENC, "engine is built for 80 mels x 1500 positions");
+  WISB_REQUIRE(d.n_text_ctx <= T_MAX, "n_text_ctx > 448");
+  WISB_REQUIRE(d.n_langs <= 128, "more than 128 languages");
+}
+
+void finish_create(wisb_handle* h) {
+  const Dims& d = h->dims;
+  const bool has_model = h->blob != nullptr;
+  cudaDeviceProp prop;
+  WISB_CUDA(cudaGetDeviceProperties(&prop, h->device));
+  WISB_REQUIRE(prop.major == 10, "libwisb200 is built for sm_100a (Blackwell B200) only");
+  h->num_sms = prop.multiProcessorCount;
+  WISB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev) WISB_CUDA(cudaEventCreate(&e));
+  h->lm_tables.ensure(logmel_table_floats());
+  logmel_init_tables(h->lm_tables.p, h->stream);
+  if (!has_model) {  // front-end-only handle (wisb_create_frontend)
+    WISB_CUDA(cudaStreamSynchronize(h->stream));
+    return;
+  }
+  // per-layer decoder weight pointers
+  h->dec_w.resize(d.n_dec_layers);
+  for (int i = 0; i < d.n_dec_layers; ++i) {
+    const std::string p = "dec." + std::to_string(i) + ".";
+    DecLayerW& w = h->dec_w[i];
+    w.ln1g = h->F(p + "ln1.g"); w.ln1b = h->F(p + "ln1.b");
+    w.qkvw = h->H(p + "qkv.w"); w.qkvb = h->F(p + "qkv.b");
+    w.ow = h->H(p + "o.w"); w.ob = h->F(p + "o.b");
+    w.ln2g = h->F(p + "ln2.g"); w.ln2b = h->F(p + "ln2.b");
+    w.cqw = h->H(p + "cq.w"); w.cqb = h->F(p + "cq.b");
+    w.cow = h->H(p + "co.w"); w.cob = h->F(p + "co.b");
+    w.ln3g = h->F(p + "ln3.g"); w.ln3b = h->F(p + "ln3.b");
+    w.fc1w = h->H(p + "fc1.w"); w.fc1b = h->F(p + "fc1.b");
+    w.fc2w = h->H(p + "fc2.w"); w.fc2b = h->F(p + "fc2.b");
+  }
+  // suppression mask: bit0 = always (suppress_ids), bit1 = at the first generated step (suppress_ids_begin)
+  std::vector<uint8_t> mask(d.n_vocab, 0);
+  auto fetch_ids = [&](const char* name) {
+    const TensorRef& t = h->T(name);
+    std::vector<int> ids(static_cast<size_t>(t.numel()));
+    if (!ids.empty()) WISB_CUDA(cudaMemcpy(ids.data(), t.ptr, ids.size() * 4, cudaMemcpyDeviceToHost));
+    return ids;
+  };
+  for (int id : fetch_ids("meta.suppress_ids"))
+    if (id >= 0 && id < d.n_vocab) mask[id] |= 1;
+  for (int id : fetch_ids("meta.suppress_ids_begin"))
+    if (id >= 0 && id < d.n_vocab) mask[id] |= 2;
+  h->mask_base.ensure(d.n_vocab);
+  h->mask_cur.ensure(d.n_vocab);
+  WISB_CUDA(cudaMemcpy(h->mask_base.p, mask.data(), mask.size(), cudaMemcpyHostToDevice));
+  WISB_CUDA(cudaMemcpy(h->mask_cur.p, mask.data(), mask.size(), cudaMemcpyHostToDevice));
+  // decoder workspaces for DEC_MAX_ROWS rows
+  const size_t R = DEC_MAX_ROWS;
+  h->dx.ensure(R * d.d_model, true);
+  h->dq.ensure(R * d.d_model, true);
+  h->dctx.ensure(R * d.d_model, true);
+  h->dh.ensure(R * 4 * d.d_model, true);
+  h->logits.ensure(R * d.n_vocab_pad, true);
+  const size_t cache = static_cast<size_t>(d.n_dec_layers) * R * T_MAX * d.d_model;
+  h->kcache.ensure(cache, true);
+  h->vcache.ensure(cache, true);
+  h->row_lse.ensure(R); h->cum.ensure(R);
+  h->part.ensure(R * TOPK_CHUNKS * MAX_CAND);
+  h->cand_score.ensure(R * MAX_CAND); h->cand_idx.ensure(R * MAX_CAND);
+  h->tokens.ensure(R);
+  h->seq0.ensure(R * T_MAX, true); h->seq1.ensure(R * T_MAX, true);
+  h->ind0.ensure(R * T_MAX, true); h->ind1.ensure(R * T_MAX, true);
+  h->flip.ensure(1, true);
+  h->done.ensure(R); h->n_hyp.ensure(R); h->best_score.ensure(R); h->best_len.ensure(R);
+  h->best_tokens.ensure(R * T_MAX, true);
+  h->prompt_dev.ensure(R * T_MAX);
+  h->st.ensure(1, true);
+  h->lang_probs.ensure(R * 128);
+  h->pin_i.ensure(4 + R * (T_MAX + 2));
+  h->pin_f.ensure(R * 130);
+  WISB_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+void ensure_encoder(wisb_handle* h, int B) {
+  if (h->blob == nullptr) {  // front-end-only handle: just the feature buffers
+    h->mel.ensure(static_cast<size_t>(B) * N_MELS * N_FRAMES);
+    h->lm_max.ensure(B);
+    return;
+  }
+  const Dims& dm = h->dims;
+  const int d = dm.d_model, H = dm.n_heads;
+  const long long M = static_cast<long long>(B) * T_ENC_PAD;
+  if (B > h->enc_cap) {
+    h->plans_B = 0;
+    h->mel.ensure(static_cast<size_t>(B) * N_MELS * N_FRAMES);
+    h->h1.release();
+    h->h1.ensure((static_cast<size_t>(B) * H1_ROWS + 8) * d, true);
+    h->x.ensure(M * d, true);
+    h->xn.ensure(M * d, true);
+    h->qkv.ensure(M * 3 * d, true);
+    h->vt.ensure(M * d, true);
+    h->ctx.ensure(M * d, true);
+    h->hbuf.ensure(M * 4 * d, true);
+    h->enc_out.ensure(M * d, true);
+    h->ckv.ensure(static_cast<size_t>(dm.n_dec_layers) * 2 * M * d, true);
+    h->lm_max.ensure(B);
+    h->enc_cap = B;
+  }
+  if (h->plans_B == B && h->plans_vmn == h->attn_v_mn) return;
+  const int Mi = static_cast<int>(M);
+  {
+    GemmEpi e;
+    e.mode = EPI_CONV2;
+    e.bias = h->F("enc.conv2.b");
+    e.out = h->x.p;
+    e.ldo = d;
+    e.pos = h->F("enc.pos");
+    gemm_plan(h->plan_conv2, h->h1.p, 2LL * d, h->H("enc.conv2.w"), Mi, d, 3 * d, e, h->num_sms, 0, 2 * d);
+  }
+  h->enc_plans.assign(dm.n_enc_layers, EncLayerPlans());
+  for (int i = 0; i < dm.n_enc_layers; ++i) {
+    const std::string p = "enc." + std::to_string(i) + ".";
+    EncLayerPlans& pl = h->enc_plans[i];
+    GemmEpi e;
+    e.mode = h->attn_v_mn ? EPI_F16 : EPI_QKV_VT;
+    e.bias = h->F(p + "qkv.b");
+    e.out = h->qkv.p;
+    e.ldo = 3 * d;
+    e.aux = h->vt.p;
+    e.d_model = d;
+    e.n_heads = H;
+    e.batch = B;
+    gemm_plan(pl.qkv, h->xn.p, d, h->H(p + "qkv.w"), Mi, 3 * d, d, e, h->num_sms);
+    GemmEpi eo;
+    eo.mode = EPI_RESID_F32;
+    eo.bias = h->F(p + "o.b");
+    eo.out = h->x.p;
+    eo.ldo = d;
+    gemm_plan(pl.o, h->ctx.p, d, h->H(p + "o.w"), Mi, d, d, eo, h->num_sms);
+    GemmEpi e1;
+    e1.mode = EPI_F16_GELU;
+    e1.bias = h->F(p + "fc1.b");
+    e1.out = h->hbuf.p;
+    e1.ldo = 4 * d;
+    gemm_plan(pl.fc1, h->xn.p, d, h->H(p + "fc1.w"), Mi, 4 * d, d, e1, h->num_sms);
+    GemmEpi e2;
+    e2.mode = EPI_RESID_F32;
+    e2.bias = h->F(p + "fc2.b");
+    e2.out = h->x.p;
+    e2.ldo = d;
+    gemm_plan(pl.fc2, h->hbuf.p, 4LL * d, h->H(p + "fc2.w"), Mi, d, 4 * d, e2, h->num_sms);
+  }
+  {
+    GemmEpi e;
+    e.mode = EPI_CROSSKV;
+    e.bias = h->F("dec.crosskv.b");
+    e.out = h->ckv.p;
+    e.d_model = d;
+    e.n_heads = H;
+    e.batch = B;
+    gemm_plan(h->plan_ckv, h->enc_out.p, d, h->H("dec.crosskv.w"), Mi, dm.n_dec_layers * 2 * d, d, e, h->num_sms);
+  }
+  enc_attn_plan(h->attn_plan, h->qkv.p, h->vt.p, h->ctx.p, B, d, H, h->attn_v_mn != 0);
+  h->plans_B = B;
+  h->plans_vmn = h->attn_v_mn;
+}
+
+// mel (device, [B,80,3000]) -> enc_out fp16 [B*1536, d] (+ cross K/V when with_ckv)
+void run_encoder(wisb_handle* h, int B, int n_layers, bool with_ckv) {
+  const Dims& dm = h->dims;
+  const int d = dm.d_model;
+  const int M = B * T_ENC_PAD;
+  cudaStream_t s = h->stream;
+  ensure_encoder(h, B);
+  conv1_gelu_run(h->mel.p, h->H("enc.conv1.w"), h->F("enc.conv1.b"), h->h1.p, B, d, s);
+  gemm_run(h->plan_conv2, s);
+  const int nl = (n_layers < 0 || n_layers > dm.n_enc_layers) ? dm.n_enc_layers : n_layers;
+  for (int i = 0; i < nl; ++i) {
+    const std::string p = "enc." + std::to_string(i) + ".";
+    EncLayerPlans& pl = h->enc_plans[i];
+    layernorm_f32_to_f16_run(h->x.p, h->F(p + "ln1.g"), h->F(p + "ln1.b"), h->xn.p, M, d, s);
+    gemm_run(pl.qkv, s);
+    if (h->attn_ref)
+      enc_attn_ref_run(h->qkv.p, h->ctx.p, B, d, dm.n_heads, s);
+    else
+      enc_attn_run(h->attn_plan, s);
+    gemm_run(pl.o, s);
+    layernorm_f32_to_f16_run(h->x.p, h->F(p + "ln2.g"), h->F(p + "ln2.b"), h->xn.p, M, d, s);
+    gemm_run(pl.fc1, s);
+    gemm_run(pl.fc2, s);
+  }
+  layernorm_f32_to_f16_run(h->x.p, h->F("enc.ln_post.g"), h->F("enc.ln_post.b"), h->enc_out.p, M, d, s);
+  h->launches += 2 + 7 * nl + 1;
+  if (with_ckv) {
+    WISB_CUDA(cudaEventRecord(h->ev[3], s));
+    gemm_run(h->plan_ckv, s);
+    h->launches += 1;
+  }
+}
+
+void upload_mel(wisb_handle* h, const float* mel, int B) {
+  ensure_encoder(h, B);
+  if (mel != nullptr) {
+    WISB_CUDA(cudaMemcpyAsync(h->mel.p, mel, static_cast<size_t>(B) * N_MELS * N_FRAMES * sizeof(float),
+                              cudaMemcpyHostToDevice, h->stream));
+    h->mel_B = B;
+  } else {
+    WISB_REQUIRE(h->mel_B == B, "mel == NULL but wisb_logmel(keep_on_device) did not leave features for this batch size");
+  }
+}
+
+struct DecodeCfg {
+  int u0, n_utt, B_total, beam, prompt_len, max_new, max_hyp;
+  float lp;
+};
+
+SearchArgs make_search_args(wisb_handle* h, const DecodeCfg& c) {
+  const Dims& dm = h->dims;
+  SearchArgs a;
+  a.logits = h->logits.p;
+  a.ldl = dm.n_vocab_pad;
+  a.n_vocab = dm.n_vocab;
+  a.mask = h->mask_cur.p;
+  a.n_utt = c.n_utt;
+  a.beam = c.beam;
+  a.n_cand = 2 * c.beam;
+  a.max_new = c.max_new;
+  a.max_hyp = c.max_hyp;
+  a.eot = dm.eot;
+  a.t_max = T_MAX;
+  a.prompt_len = c.prompt_len;
+  a.length_penalty = c.lp;
+  a.row_lse = h->row_lse.p;
+  a.cum = h->cum.p;
+  a.part = h->part.p;
+  a.cand_score = h->cand_score.p;
+  a.cand_idx = h->cand_idx.p;
+  a.tokens = h->tokens.p;
+  a.seq[0] = h->seq0.p;
+  a.seq[1] = h->seq1.p;
+  a.indir[0] = h->ind0.p;
+  a.indir[1] = h->ind1.p;
+  a.flip = h->flip.p;
+  a.done = h->done.p;
+  a.n_hyp = h->n_hyp.p;
+  a.best_score = h->best_score.p;
+  a.best_len = h->best_len.p;
+  a.best_tokens = h->best_tokens.p;
+  a.st = h->st.p;
+  return a;
+}
+
+// one decoder forward for R rows at position st->pos; returns kernels launched
+int enqueue_decoder_forward(wisb_handle* h, const DecodeCfg& c, bool with_logits) {
+  const Dims& dm = h->dims;
+  const int d = dm.d_model, H = dm.n_heads, R = c.n_utt * c.beam;
+  cudaStream_t s = h->stream;
+  const DecState* st = h->st.p;
+  int n = 0;
+  dec_embed_run(h->tokens.p, h->H("dec.tok_emb"), h->F("dec.pos"), h->dx.p, R, d, st, s);
+  ++n;
+  const size_t layer_cache = static_cast<size_t>(DEC_MAX_ROWS) * T_MAX * d;
+  const size_t head_block = static_cast<size_t>(H) * T_ENC_PAD * HEAD_DIM;  // one utterance, one of K/V
+  for (int i = 0; i < dm.n_dec_layers; ++i) {
+    const DecLayerW& w = h->dec_w[i];
+    GemvArgs g;
+    g.R = R;
+    g.st = st;
+    // LN1 + QKV (+ cache append)
+    g.x = h->dx.p; g.ln_g = w.ln1g; g.ln_b = w.ln1b; g.w = w.qkvw; g.bias = w.qkvb;
+    g.out = h->dq.p; g.ldo = d; g.N = 3 * d; g.K = d; g.epi = GV_QKV;
+    g.kcache = h->kcache.p + i * layer_cache; g.vcache = h->vcache.p + i * layer_cache; g.d_model = d; g.t_max = T_MAX;
+    gemv_run(g, s);
+    dec_self_attn_run(h->dq.p, h->kcache.p + i * layer_cache, h->vcache.p + i * layer_cache, h->ind0.p, h->ind1.p,
+                      h->flip.p, h->dctx.p, R, d, H, T_MAX, st, s);
+    GemvArgs o;
+    o.R = R; o.st = st; o.x = h->dctx.p; o.w = w.ow; o.bias = w.ob; o.out = h->dx.p; o.ldo = d; o.N = d; o.K = d;
+    o.epi = GV_RESID;
+    gemv_run(o, s);
+    // LN2 + cross-attention
+    GemvArgs q;
+    q.R = R; q.st = st; q.x = h->dx.p; q.ln_g = w.ln2g; q.ln_b = w.ln2b; q.w = w.cqw; q.bias = w.cqb; q.out = h->dq.p;
+    q.ldo = d; q.N = d; q.K = d; q.epi = GV_STORE;
+    gemv_run(q, s);
+    const __half* kl = h->ckv.p + (static_cast<size_t>(i * 2 + 0) * c.B_total + c.u0) * head_block;
+    const __half* vl = h->ckv.p + (static_cast<size_t>(i * 2 + 1) * c.B_total + c.u0) * head_block;
+    dec_cross_attn_run(h->dq.p, kl, vl, h->dctx.p, c.n_utt, c.beam, d, H, s);
+    GemvArgs co;
+    co.R = R; co.st = st; co.x = h->dctx.p; co.w = w.cow; co.bias = w.cob; co.out = h->dx.p; co.ldo = d; co.N = d;
+    co.K = d; co.epi = GV_RESID;
+    gemv_run(co, s);
+    // LN3 + MLP
+    GemvArgs f1;
+    f1.R = R; f1.st = st; f1.x = h->dx.p; f1.ln_g = w.ln3g; f1.ln_b = w.ln3b; f1.w = w.fc1w; f1.bias = w.fc1b;
+    f1.out = h->dh.p; f1.ldo = 4 * d; f1.N = 4 * d; f1.K = d; f1.epi = GV_GELU;
+    gemv_run(f1, s);
+    GemvArgs f2;
+    f2.R = R; f2.st = st; f2.x = h->dh.p; f2.w = w.fc2w; f2.bias = w.fc2b; f2.out = h->dx.p; f2.ldo = d; f2.N = d;
+    f2.K = 4 * d; f2.epi = GV_RESID;
+    gemv_run(f2, s);
+    n += 8;
+  }
+  if (with_logits) {
+    GemvArgs v;
+    v.R = R; v.st = st; v.x = h->dx.p; v.ln_g = h->F("dec.ln.g"); v.ln_b = h->F("dec.ln.b"); v.w = h->H("dec.tok_emb");
+    v.out = h->logits.p; v.ldo = dm.n_vocab_pad; v.N = dm.n_vocab; v.K = d; v.epi = GV_STORE;
+    gemv_run(v, s);
+    ++n;
+  }
+  return n;
+}
+
+void enqueue_prefill(wisb_handle* h, const DecodeCfg& c) {
+  enqueue_decoder_forward(h, c, false);
+  prefill_advance_run(h->tokens.p, h->prompt_dev.p, c.prompt_len, c.n_utt * c.beam, c.beam, h->st.p, h->stream);
+}
+void enqueue_step(wisb_handle* h, const DecodeCfg& c) {
+  enqueue_decoder_forward(h, c, true);
+  search_step_run(make_search_args(h, c), h->stream);
+}
+
+DecGraphs& get_graphs(wisb_handle* h, const DecodeCfg& c) {
+  GraphKey key;
+  memset(&key, 0, sizeof(key));
+  key.n_utt = c.n_utt; key.beam = c.beam; key.prompt_len = c.prompt_len; key.max_new = c.max_new;
+  key.max_hyp = c.max_hyp; key.lp = c.lp;
+  key.u0 = c.u0; key.b_total = c.B_total;  // they move the cross-K/V base pointers baked into the graph
+  auto it = h->graphs.find(key);
+  if (it != h->graphs.end()) return it->second;
+  if (h->graphs.size() > 64) {  // bound the cache
+    for (auto& kv : h->graphs) {
+      if (kv.second.prefill) cudaGraphExecDestroy(kv.second.prefill);
+      if (kv.second.step) cudaGraphExecDestroy(kv.second.step);
+    }
+    h->graphs.clear();
+  }
+  DecGraphs g;
+  cudaGraph_t graph;
+  WISB_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  enqueue_prefill(h, c);
+  WISB_CUDA(cudaStreamEndCapture(h->stream, &graph));
+  WISB_CUDA(cudaGraphInstantiate(&g.prefill, graph, 0));
+  WISB_CUDA(cudaGraphDestroy(graph));
+  WISB_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  enqueue_step(h, c);
+  WISB_CUDA(cudaStreamEndCapture(h->stream, &graph));
+  WISB_CUDA(cudaGraphInstantiate(&g.step, graph, 0));
+  WISB_CUDA(cudaGraphDestroy(graph));
+  return h->graphs[key] = g;
+}
+
+void set_extra_suppress(wisb_handle* h, const int32_t* extra, int n_extra) {
+  std::vector<int> want(extra ? extra : nullptr, extra ? extra + n_extra : nullptr);
+  if (want == h->mask_extra) return;
+  const Dims& dm = h->dims;
+  WISB_CUDA(cudaMemcpyAsync(h->mask_cur.p, h->mask_base.p, dm.n_vocab, cudaMemcpyDeviceToDevice, h->stream));
+  if (!want.empty()) {
+    std::vector<uint8_t> m(dm.n_vocab);
+    WISB_CUDA(cudaMemcpyAsync(m.data(), h->mask_base.p, dm.n_vocab, cudaMemcpyDeviceToHost, h->stream));
+    WISB_CUDA(cudaStreamSynchronize(h->stream));
+    for (int id : want) {
+      WISB_REQUIRE(id >= 0 && id < dm.n_vocab, "suppress token id outside the vocabulary");
+      m[id] |= 1;
+    }
+    WISB_CUDA(cudaMemcpyAsync(h->mask_cur.p, m.data(), dm.n_vocab, cudaMemcpyHostToDevice, h->stream));
+    WISB_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  h->mask_extra = want;
+}
+
+// decode utterances [u0, u0 + n_utt) of the encoded batch; writes results to the host arrays
+int decode_pass(wisb_handle* h, const DecodeCfg& c, const int32_t* prompts, int32_t* out_ids, int out_stride,
+                int32_t* out_len, float* out_score) {
+  cudaStream_t s = h->stream;
+  const int R = c.n_utt * c.beam;
+  int steps = 0;
+  // prompts for this pass
+  memcpy(h->pin_i.p + 4, prompts + static_cast<size_t>(c.u0) * c.prompt_len, sizeof(int) * c.n_utt * c.prompt_len);
+  WISB_CUDA(cudaMemcpyAsync(h->prompt_dev.p, h->pin_i.p + 4, sizeof(int) * c.n_utt * c.prompt_len, cudaMemcpyHostToDevice, s));
+  SearchArgs sa = make_search_args(h, c);
+  search_init_run(sa, h->prompt_dev.p, s);
+  if (c.max_new > 0) {
+    DecGraphs* g = h->use_graphs ? &get_graphs(h, c) : nullptr;
+    for (int p = 0; p + 1 < c.prompt_len; ++p) {
+      if (g) WISB_CUDA(cudaGraphLaunch(g->prefill, s)); else enqueue_prefill(h, c);
+      ++steps;
+    }
+    const int per_step = 1 + 8 * h->dims.n_dec_layers + 1 + 5;
+    h->launches += (c.prompt_len - 1) * (per_step - 5);
+    volatile int* flag = h->pin_i.p;
+    *flag = 0;
+    for (int gs = 0; gs < c.max_new; ++gs) {
+      if (g) WISB_CUDA(cudaGraphLaunch(g->step, s)); else enqueue_step(h, c);
+      ++steps;
+      h->launches += per_step;
+      const bool poll = ((gs + 1) % h->decode_poll == 0) || gs + 1 == c.max_new;
+      if (poll) {
+        WISB_CUDA(cudaMemcpyAsync(const_cast<int*>(flag), &h->st.p->all_done, sizeof(int), cudaMemcpyDeviceToHost, s));
+        WISB_CUDA(cudaStreamSynchronize(s));
+        if (*flag) break;
+      }
+    }
+  }
+  // results
+  int* lens = h->pin_i.p + 4;
+  int* toks = lens + DEC_MAX_ROWS;
+  WISB_CUDA(cudaMemcpyAsync(lens, h->best_len.p, sizeof(int) * c.n_utt, cudaMemcpyDeviceToHost, s));
+  WISB_CUDA(cudaMemcpyAsync(toks, h->best_tokens.p, sizeof(int) * c.n_utt * (c.max_new > 0 ? c.max_new : 1), cudaMemcpyDeviceToHost, s));
+  WISB_CUDA(cudaMemcpyAsync(h->pin_f.p, h->best_score.p, sizeof(float) * c.n_utt, cudaMemcpyDeviceToHost, s));
+  WISB_CUDA(cudaStreamSynchronize(s));
+  for (int u = 0; u < c.n_utt; ++u) {
+    const int len = c.max_new > 0 ? lens[u] : 0;
+    out_len[c.u0 + u] = len;
+    for (int t = 0; t < len && t < out_stride; ++t) out_ids[static_cast<size_t>(c.u0 + u) * out_stride + t] = toks[u * c.max_new + t];
+    if (out_score) out_score[c.u0 + u] = c.max_new > 0 ? h->pin_f.p[u] : 0.f;
+  }
+  (void)R;
+  return steps;
+}
+
+template <typename Fn>
+int guarded(wisb_handle* h, Fn&& fn) {
+  try {
+    if (h == nullptr) throw Error(1, "null handle");
+    std::lock_guard<std::mutex> lock(h->mu);
+    WISB_CUDA(cudaSetDevice(h->device));
+    fn();
+    return 0;
+  } catch (const Error& e) {
+    g_last_error = e.what();
+    if (h && h->stream) {  // leave no dangling capture / sticky state behind
+      cudaStreamCaptureStatus cs;
+      if (cudaStreamIsCapturing(h->stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) {
+        cudaGraph_t g = nullptr;
+        cudaStreamEndCapture(h->stream, &g);
+        if (g) cudaGraphDestroy(g);
+      }
+      cudaGetLastError();
+    }
+    return e.code;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return 2;
+  }
+}
+
+int create_common(wisb_handle** out, int device, const std::function<void(wisb_handle*)>& load) {
+  if (out == nullptr) {
+    g_last_error = "out handle pointer is NULL";
+    return 1;
+  }
+  *out = nullptr;
+  std::unique_ptr<wisb_handle> h(new wisb_handle());
+  try {
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+      throw Error(2, std::string("no CUDA device available (libwisb200 has no CPU fallback): ") + cudaGetErrorString(e));
+    WISB_REQUIRE(device >= 0 && device < n_dev, "device index out of range");
+    h->device = device;
+    WISB_CUDA(cudaSetDevice(device));
+    load(h.get());
+    finish_create(h.get());
+    *out = h.release();
+    return 0;
+  } catch (const Error& e) {
+    g_last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return 2;
+  }
+}
+
+}  // namespace
+
+// ===================================================================================================================== C ABI
+extern "C" {
+
+int wisb_abi_version(void) { return WISB_ABI_VERSION; }
+const char* wisb_last_error(void) { return g_last_error.c_str(); }
+
+int wisb_create_from_host(const void* blob, size_t nbytes, int device, wisb_handle** out) {
+  return create_common(out, device, [&](wisb_handle* h) {
+    WISB_REQUIRE(blob != nullptr && nbytes >= 256, "weight blob is NULL or too small");
+    h->blob_bytes = nbytes;
+    h->own_blob = true;
+    WISB_CUDA(cudaMalloc(&h->blob, nbytes));
+    WISB_CUDA(cudaMemcpy(h->blob, blob, nbytes, cudaMemcpyHostToDevice));
+    const uint8_t* b = static_cast<const uint8_t*>(blob);
+    uint32_t n_tensors = 0;
+    memcpy(&n_tensors, b + 12, 4);
+    const size_t head = 256 + 96ull * n_tensors;
+    WISB_REQUIRE(head <= nbytes, "truncated weight blob");
+    parse_blob(h, std::vector<uint8_t>(b, b + head));
+  });
+}
+
+int wisb_create(const char* weights_path, int device, wisb_handle** out) {
+  if (weights_path == nullptr) {
+    g_last_error = "weights_path is NULL";
+    return 1;
+  }
+  FILE* f = fopen(weights_path, "rb");
+  if (!f) {
+    g_last_error = std::string("cannot open weight blob '") + weights_path + "'";
+    return 1;
+  }
+  fseek(f, 0, SEEK_END);
+  const long long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<uint8_t> buf(static_cast<size_t>(sz > 0 ? sz : 0));
+  const size_t got = buf.empty() ? 0 : fread(buf.data(), 1, buf.size(), f);
+  fclose(f);
+  if (got != buf.size()) {
+    g_last_error = "short read on the weight blob";
+    return 1;
+  }
+  return wisb_create_from_host(buf.data(), buf.size(), device, out);
+}
+
+int wisb_create_from_device(const void* device_blob, size_t nbytes, int device, wisb_handle** out) {
+  return create_common(out, device, [&](wisb_handle* h) {
+    WISB_REQUIRE(device_blob != nullptr && nbytes >= 256, "weight blob is NULL or too small");
+    h->blob_bytes = nbytes;
+    h->own_blob = false;
+    h->blob = const_cast<uint8_t*>(static_cast<const uint8_t*>(device_blob));
+    std::vector<uint8_t> head(256);
+    WISB_CUDA(cudaMemcpy(head.data(), h->blob, 256, cudaMemcpyDeviceToHost));
+    uint32_t n_tensors = 0;
+    memcpy(&n_tensors, head.data() + 12, 4);
+    const size_t hb = 256 + 96ull * n_tensors;
+    WISB_REQUIRE(hb <= nbytes, "truncated weight blob");
+    head.resize(hb);
+    WISB_CUDA(cudaMemcpy(head.data(), h->blob, hb, cudaMemcpyDeviceToHost));
+    parse_blob(h, head);
+  });
+}
+
+int wisb_create_frontend(int device, wisb_handle** out) {
+  return create_common(out, device, [&](wisb_handle*) {});
+}
+
+int wisb_destroy(wisb_handle* h) {
+  if (h == nullptr) return 0;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto& kv : h->graphs) {
+    if (kv.second.prefill) cudaGraphExecDestroy(kv.second.prefill);
+    if (kv.second.step) cudaGraphExecDestroy(kv.second.step);
+  }
+  for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+  if (h->own_blob && h->blob) cudaFree(h->blob);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+int wisb_get_dims(wisb_handle* h, int32_t* dims) {
+  return guarded(h, [&] {
+    WISB_REQUIRE(dims != nullptr, "dims is NULL");
+    memcpy(dims, &h->dims, sizeof(Dims));
+  });
+}
+
+int wisb_set_option(wisb_handle* h, const char* key, int value) {
+  return guarded(h, [&] {
+    WISB_REQUIRE(key != nullptr, "key is NULL");
+    const std::string k(key);
+    if (k == "use_graphs") h->use_graphs = value;
+    else if (k == "attn_v_mn_major") h->attn_v_mn = value;
+    else if (k == "attn_ref") h->attn_ref = value;
+    else if (k == "decode_poll") h->decode_poll = value < 1 ? 1 : value;
+    else throw Error(1, "unknown option '" + k + "'");
+  });
+}
+
+int wisb_get_timing(wisb_handle* h, float* out8) {
+  return guarded(h, [&] {
+    WISB_REQUIRE(out8 != nullptr, "out is NULL");
+    memcpy(out8, h->timing, sizeof(h->timing));
+  });
+}
+
+int wisb_logmel(wisb_handle* h, const void* pcm, int pcm_dtype, int pcm_on_device, const int64_t* offsets,
+                const int32_t* n_samples, int B, float* mel_out, int keep_on_device) {
+  return guarded(h, [&] {
+    WISB_REQUIRE(pcm != nullptr && offsets != nullptr && n_samples != nullptr, "pcm / offsets / n_samples is NULL");
+    WISB_REQUIRE(B >= 1 && B <= 4096, "B out of range");
+    WISB_REQUIRE(pcm_dtype == WISB_PCM_F32 || pcm_dtype == WISB_PCM_S16, "pcm_dtype must be WISB_PCM_F32 or WISB_PCM_S16");
+    const size_t esz = pcm_dtype == WISB_PCM_S16 ? 2 : 4;
+    long long total = 0;
+    for (int b = 0; b < B; ++b) {
+      WISB_REQUIRE(n_samples[b] >= 0 && offsets[b] >= 0, "negative n_samples / offset");
+      const long long end = offsets[b] + n_samples[b];
+      if (end > total) total = end;
+    }
+    cudaStream_t s = h->stream;
+    ensure_encoder(h, B);
+    h->pcm_off.ensure(B);
+    h->pcm_n.ensure(B);
+    WISB_CUDA(cudaEventRecord(h->ev[0], s));
+    const void* pcm_d = pcm;
+    if (!pcm_on_device) {
+      h->pcm_dev.ensure(static_cast<size_t>(total > 0 ? total : 1) * esz);
+      if (total > 0) WISB_CUDA(cudaMemcpyAsync(h->pcm_dev.p, pcm, static_cast<size_t>(total) * esz, cudaMemcpyHostToDevice, s));
+      pcm_d = h->pcm_dev.p;
+    }
+    static_assert(sizeof(long long) == sizeof(int64_t), "offset type");
+    WISB_CUDA(cudaMemcpyAsync(h->pcm_off.p, offsets, sizeof(int64_t) * B, cudaMemcpyHostToDevice, s));
+    WISB_CUDA(cudaMemcpyAsync(h->pcm_n.p, n_samples, sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
+    logmel_run(pcm_d, pcm_dtype == WISB_PCM_S16, h->pcm_off.p, h->pcm_n.p, B, h->lm_tables.p, h->mel.p, h->lm_max.p, s);
+    if (mel_out != nullptr)
+      WISB_CUDA(cudaMemcpyAsync(mel_out, h->mel.p, static_cast<size_t>(B) * N_MELS * N_FRAMES * sizeof(float), cudaMemcpyDeviceToHost, s));
+    WISB_CUDA(cudaEventRecord(h->ev[1], s));
+    WISB_CUDA(cudaStreamSynchronize(s));
+    WISB_CUDA(cudaEventElapsedTime(&h->timing[0], h->ev[0], h->ev[1]));
+    h->mel_B = keep_on_device ? B : 0;
+  });
+}
+
+int wisb_generate(wisb_handle* h, const float* mel, int B, const int32_t* prompts, int prompt_len, int beam_size,
+                  float patience, float length_penalty, int max_length, const int32_t* extra_suppress, int n_extra,
+                  int32_t* out_ids, int out_stride, int32_t* out_len, float* out_score) {
+  return guarded(h, [&] {
+    const Dims& dm = h->dims;
+    WISB_REQUIRE(h->blob != nullptr, "handle has no model (created by wisb_create_frontend)");
+    WISB_REQUIRE(B >= 1 && B <= 4096, "B out of range");
+    WISB_REQUIRE(prompts != nullptr && out_ids != nullptr && out_len != nullptr, "prompts / out_ids / out_len is NULL");
+    WISB_REQUIRE(beam_size >= 1 && beam_size <= MAX_BEAM, "beam_size must be in [1, 8]");
+    WISB_REQUIRE(prompt_len >= 1 && prompt_len <= dm.n_text_ctx, "prompt length out of range");
+    WISB_REQUIRE(max_length >= 1 && max_length <= dm.n_text_ctx, "max_length must be in [1, n_text_ctx]");
+    WISB_REQUIRE(patience > 0.f, "patience must be positive");
+    WISB_REQUIRE(n_extra >= 0 && (n_extra == 0 || extra_suppress != nullptr), "bad extra_suppress");
+    for (long long i = 0; i < static_cast<long long>(B) * prompt_len; ++i)
+      WISB_REQUIRE(prompts[i] >= 0 && prompts[i] < dm.n_vocab, "prompt token outside the vocabulary");
+    int max_new = max_length / 2 < max_length - prompt_len ? max_length / 2 : max_length - prompt_len;
+    if (max_new < 0) max_new = 0;
+    WISB_REQUIRE(out_stride >= max_new, "out_stride smaller than the maximum number of generated tokens");
+    cudaStream_t s = h->stream;
+    h->launches = 0;
+    WISB_CUDA(cudaEventRecord(h->ev[0], s));
+    upload_mel(h, mel, B);
+    set_extra_suppress(h, extra_suppress, n_extra);
+    WISB_CUDA(cudaEventRecord(h->ev[2], s));
+    run_encoder(h, B, -1, true);
+    WISB_CUDA(cudaEventRecord(h->ev[4], s));
+    const int per_pass = DEC_MAX_ROWS / beam_size;
+    int steps = 0;
+    for (int u0 = 0; u0 < B; u0 += per_pass) {
+      DecodeCfg c;
+      c.u0 = u0;
+      c.n_utt = (B - u0 < per_pass) ? B - u0 : per_pass;
+      c.B_total = B;
+      c.beam = beam_size;
+      c.prompt_len = prompt_len;
+      c.max_new = max_new;
+      c.max_hyp = static_cast<int>(beam_size * patience + 0.5f);
+      if (c.max_hyp < 1) c.max_hyp = 1;
+      c.lp = length_penalty;
+      steps += decode_pass(h, c, prompts, out_ids, out_stride, out_len, out_score);
+    }
+    WISB_CUDA(cudaEventRecord(h->ev[5], s));
+    WISB_CUDA(cudaStreamSynchronize(s));
+    WISB_CUDA(cudaEventElapsedTime(&h->timing[1], h->ev[0], h->ev[2]));
+    WISB_CUDA(cudaEventElapsedTime(&h->timing[2], h->ev[2], h->ev[3]));
+    WISB_CUDA(cudaEventElapsedTime(&h->timing[3], h->ev[3], h->ev[4]));
+    WISB_CUDA(cudaEventElapsedTime(&h->timing[4], h->ev[4], h->ev[5]));
+    WISB_CUDA(cudaEventElapsedTime(&h->timing[5], h->ev[0], h->ev[5]));
+    h->timing[6] = static_cast<float>(steps);
+    h->timing[7] = static_cast<float>(h->launches);
+  });
+}
+
+int wisb_detect_language(wisb_handle* h, const float* mel, int B, int32_t* lang_ids_out, float* probs_out) {
+  return guarded(h, [&] {
+    const Dims& dm = h->dims;
+    WISB_REQUIRE(h->blob != nullptr, "handle has no model (created by wisb_create_frontend)");
+    WISB_REQUIRE(B >= 1 && B <= 4096, "B out of range");
+    WISB_REQUIRE(lang_ids_out != nullptr && probs_out != nullptr, "output pointer is NULL");
+    cudaStream_t s = h->stream;
+    upload_mel(h, mel, B);
+    run_encoder(h, B, -1, true);
+    const int nl = dm.n_langs;
+    h->lang_ids.ensure(nl);
+    std::vector<int> ids(nl);
+    for (int i = 0; i < nl; ++i) ids[i] = dm.lang_first + i;
+    WISB_CUDA(cudaMemcpyAsync(h->lang_ids.p, ids.data(), sizeof(int) * nl, cudaMemcpyHostToDevice, s));
+    WISB_CUDA(cudaStreamSynchronize(s));
+    std::vector<int32_t> sot(DEC_MAX_ROWS, dm.sot);
+    for (int u0 = 0; u0 < B; u0 += DEC_MAX_ROWS) {
+      DecodeCfg c;
+      c.u0 = u0;
+      c.n_utt = (B - u0 < DEC_MAX_ROWS) ? B - u0 : DEC_MAX_ROWS;
+      c.B_total = B;
+      c.beam = 1;
+      c.prompt_len = 1;
+      c.max_new = 1;
+      c.max_hyp = 1;
+      c.lp = 1.f;
+      memcpy(h->pin_i.p + 4, sot.data(), sizeof(int) * c.n_utt);
+      WISB_CUDA(cudaMemcpyAsync(h->prompt_dev.p, h->pin_i.p + 4, sizeof(int) * c.n_utt, cudaMemcpyHostToDevice, s));
+      search_init_run(make_search_args(h, c), h->prompt_dev.p, s);
+      enqueue_decoder_forward(h, c, true);
+      lang_probs_run(h->logits.p, dm.n_vocab_pad, h->lang_ids.p, nl, c.n_utt, 1, h->lang_probs.p, s);
+      WISB_CUDA(cudaMemcpyAsync(h->pin_f.p, h->lang_probs.p, sizeof(float) * c.n_utt * nl, cudaMemcpyDeviceToHost, s));
+      WISB_CUDA(cudaStreamSynchronize(s));
+      for (int u = 0; u < c.n_utt; ++u) {
+        std::vector<int> order(nl);
+        for (int i = 0; i < nl; ++i) order[i] = i;
+        const float* p = h->pin_f.p + u * nl;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return p[a] > p[b]; });
+        for (int i = 0; i < nl; ++i) {
+          lang_ids_out[static_cast<size_t>(u0 + u) * nl + i] = ids[order[i]];
+          probs_out[static_cast<size_t>(u0 + u) * nl + i] = p[order[i]];
+        }
+      }
+    }
+  });
+}
+
+// --------------------------------------------------------------------------------------------------------------------- diagnostics
+int wisb_debug_gemm(wisb_handle* h, const uint16_t* a, const uint16_t* w, float* c, int M, int N, int K, int impl, int bn) {
+  return guarded(h, [&] {
+    WISB_REQUIRE(a && w && c, "NULL pointer");
+    cudaStream_t s = h->stream;
+    DevBuf<__half> da, dw;
+    DevBuf<float> dc;
+    da.ensure(static_cast<size_t>(M) * K);
+    dw.ensure(static_cast<size_t>(N) * K);
+    dc.ensure(static_cast<size_t>(M) * N, true);
+    WISB_CUDA(cudaMemcpyAsync(da.p, a, sizeof(__half) * M * K, cudaMemcpyHostToDevice, s));
+    WISB_CUDA(cudaMemcpyAsync(dw.p, w, sizeof(__half) * N * K, cudaMemcpyHostToDevice, s));
+    if (impl == 1) {
+      gemm_ref_run(da.p, K, dw.p, dc.p, M, N, K, s);
+    } else {
+      GemmPlan p;
+      GemmEpi e;
+      e.mode = EPI_F32;
+      e.out = dc.p;
+      e.ldo = N;
+      gemm_plan(p, da.p, K, dw.p, M, N, K, e, h->num_sms, bn);
+      gemm_run(p, s);
+    }
+    WISB_CUDA(cudaMemcpyAsync(c, dc.p, sizeof(float) * M * N, cudaMemcpyDeviceToHost, s));
+    WISB_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int wisb_debug_encode(wisb_handle* h, const float* mel, int B, float* enc_out, int n_layers) {
+  return guarded(h, [&] {
+    WISB_REQUIRE(h->blob != nullptr && enc_out != nullptr && B >= 1, "bad arguments");
+    const int d = h->dims.d_model;
+    cudaStream_t s = h->stream;
+    upload_mel(h, mel, B);
+    run_encoder(h, B, n_layers, false);
+    std::vector<__half> tmp(static_cast<size_t>(B) * T_ENC_PAD * d);
+    WISB_CUDA(cudaMemcpyAsync(tmp.data(), h->enc_out.p, tmp.size() * sizeof(__half), cudaMemcpyDeviceToHost, s));
+    WISB_CUDA(cudaStreamSynchronize(s));
+    for (int b = 0; b < B; ++b)
+      for (int t = 0; t < T_ENC; ++t)
+        for (int e = 0; e < d; ++e)
+          enc_out[(static_cast<size_t>(b) * T_ENC + t) * d + e] = __half2float(tmp[(static_cast<size_t>(b) * T_ENC_PAD + t) * d + e]);
+  });
+}
+
+int wisb_debug_forced_logits(wisb_handle* h, const float* mel, const int32_t* tokens, int n_tokens, float* logits_out) {
+  return guarded(h, [&] {
+    const Dims& dm = h->dims;
+    WISB_REQUIRE(h->blob != nullptr && tokens != nullptr && logits_out != nullptr && n_tokens >= 1 && n_tokens <= dm.n_text_ctx, "bad arguments");
+    cudaStream_t s = h->stream;
+    upload_mel(h, mel, 1);
+    run_encoder(h, 1, -1, true);
+    DecodeCfg c;
+    c.u0 = 0; c.n_utt = 1; c.B_total = 1; c.beam = 1; c.prompt_len = n_tokens; c.max_new = 1; c.max_hyp = 1; c.lp = 1.f;
+    memcpy(h->pin_i.p + 4, tokens, sizeof(int) * n_tokens);
+    WISB_CUDA(cudaMemcpyAsync(h->prompt_dev.p, h->pin_i.p + 4, sizeof(int) * n_tokens, cudaMemcpyHostToDevice, s));
+    search_init_run(make_search_args(h, c), h->prompt_dev.p, s);
+    for (int p = 0; p < n_tokens; ++p) {
+      enqueue_decoder_forward(h, c, true);
+      WISB_CUDA(cudaMemcpyAsync(logits_out + static_cast<size_t>(p) * dm.n_vocab, h->logits.p, sizeof(float) * dm.n_vocab, cudaMemcpyDeviceToHost, s));
+      if (p + 1 < n_tokens) prefill_advance_run(h->tokens.p, h->prompt_dev.p, n_tokens, 1, 1, h->st.p, s);
+    }
+    WISB_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+}  // extern "C"

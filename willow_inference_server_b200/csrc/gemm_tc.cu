@@ -1,0 +1,382 @@
+// tcgen05 GEMM for sm_100a:  D[M,N] = A[M,K] . W[N,K]^T   (fp16 x fp16 -> fp32 in TMEM) with fused epilogues.
+//
+// Replaces (reference side): every dense layer CTranslate2 runs through cuBLAS `gemmEx` for
+// ctranslate2.models.Whisper.generate (/root/reference/main.py:687-692; SURVEY.md section 2b rows K3,K5,K7-K9,K11).
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer   : cp.async.bulk.tensor 128x64 (A) and BNx64 (W) fp16 tiles, 128B swizzle, STAGES-deep ring
+//   warp 1      MMA issuer     : one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per stage,
+//                                tcgen05.commit frees the smem stage / publishes the accumulator
+//   warps 2..5  epilogue       : tcgen05.ld 32x32b from the double-buffered TMEM accumulator, bias / GELU / residual /
+//                                scatter epilogues, vectorised global stores
+// The accumulator is double buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop of i+1.
+#include <mutex>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace wisb {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void store_f16x32(__half* dst, const float (&f)[32]) {
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 h0 = __floats2half2_rn(f[8 * i + 0], f[8 * i + 1]);
+    __half2 h1 = __floats2half2_rn(f[8 * i + 2], f[8 * i + 3]);
+    __half2 h2 = __floats2half2_rn(f[8 * i + 4], f[8 * i + 5]);
+    __half2 h3 = __floats2half2_rn(f[8 * i + 6], f[8 * i + 7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    u.z = *reinterpret_cast<uint32_t*>(&h2);
+    u.w = *reinterpret_cast<uint32_t*>(&h3);
+    d4[i] = u;
+  }
+}
+
+// One thread owns one output row and 32 consecutive columns [col0, col0+32).
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, int row, int col0, const uint32_t (&v)[32]) {
+  float f[32];
+  if (e.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 b = __ldg(b4 + i);
+      f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b.x;
+      f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
+      f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z;
+      f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  }
+  switch (e.mode) {
+    case EPI_F16_GELU:
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+      // fallthrough
+    case EPI_F16:
+      store_f16x32(reinterpret_cast<__half*>(e.out) + static_cast<long long>(row) * e.ldo + col0, f);
+      break;
+    case EPI_RESID_F32: {
+      float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + static_cast<long long>(row) * e.ldo + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 o = o4[i];
+        o.x += f[4 * i + 0];
+        o.y += f[4 * i + 1];
+        o.z += f[4 * i + 2];
+        o.w += f[4 * i + 3];
+        o4[i] = o;
+      }
+      break;
+    }
+    case EPI_CONV2: {
+      const int t = row % T_ENC_PAD;
+      float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + static_cast<long long>(row) * e.ldo + col0);
+      if (t < T_ENC) {
+        const float4* p4 = reinterpret_cast<const float4*>(e.pos + static_cast<long long>(t) * e.ldo + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 p = __ldg(p4 + i);
+          o4[i] = make_float4(gelu_erf(f[4 * i + 0]) + p.x, gelu_erf(f[4 * i + 1]) + p.y, gelu_erf(f[4 * i + 2]) + p.z,
+                              gelu_erf(f[4 * i + 3]) + p.w);
+        }
+      } else {  // padding rows of the window: keep them exactly zero
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      break;
+    }
+    case EPI_CROSSKV: {
+      // col -> (layer, k|v, head, e); row -> (b, t); out [layer][kv][b][head][1536][64]
+      const int two_d = 2 * e.d_model;
+      const int layer = col0 / two_d;
+      const int within = col0 - layer * two_d;
+      const int kv = within / e.d_model;
+      const int c = within - kv * e.d_model;
+      const int head = c >> 6, e0 = c & 63;
+      const int b = row / T_ENC_PAD, t = row - b * T_ENC_PAD;
+      long long idx = ((((static_cast<long long>(layer) * 2 + kv) * e.batch + b) * e.n_heads + head) * T_ENC_PAD + t) * 64 + e0;
+      store_f16x32(reinterpret_cast<__half*>(e.out) + idx, f);
+      break;
+    }
+    case EPI_QKV_VT: {
+      if (col0 < 2 * e.d_model) {
+        store_f16x32(reinterpret_cast<__half*>(e.out) + static_cast<long long>(row) * e.ldo + col0, f);
+      } else {  // V part, transposed per head: vt[((b*H + head)*64 + e)][t]
+        const int c = col0 - 2 * e.d_model;
+        const int head = c >> 6, e0 = c & 63;
+        const int b = row / T_ENC_PAD, t = row - b * T_ENC_PAD;
+        __half* vt = reinterpret_cast<__half*>(e.aux) +
+                     (static_cast<long long>(b * e.n_heads + head) * 64 + e0) * T_ENC_PAD + t;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) vt[static_cast<long long>(i) * T_ENC_PAD] = __float2half_rn(f[i]);
+      }
+      break;
+    }
+    case EPI_F32: {
+      float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + static_cast<long long>(row) * e.ldo + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o4[i] = make_float4(f[4 * i + 0], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N, int K,
+               int a_wrap, const GemmEpi epi) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;  // 128B-swizzle atoms need 1024-byte alignment
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t smem_a0 = base;
+  const uint32_t smem_b0 = base + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES));
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = M / BM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int k_blocks = K / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1) {
+    tmem_alloc<Cfg::TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile % m_tiles) * BM;
+        const int n0 = (tile / m_tiles) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
+          // a_wrap > 0: logical A row r = [phys row r | first K - a_wrap columns of phys row r + 1]  (conv2 view)
+          int ka = kb * BK, ra = m0;
+          if (a_wrap > 0 && ka >= a_wrap) {
+            ka -= a_wrap;
+            ra += 1;
+          }
+          tma_load_2d(smem_a0 + stage * A_STAGE_BYTES, &map_a, full_bar(stage), ka, ra);
+          tma_load_2d(smem_b0 + stage * Cfg::B_STAGE_BYTES, &map_b, full_bar(stage), kb * BK, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint64_t da = make_desc_sw128(smem_a0 + stage * A_STAGE_BYTES, 1024);
+          const uint64_t db = make_desc_sw128(smem_b0 + stage * Cfg::B_STAGE_BYTES, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 fp16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            umma_f16_ss(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees this smem stage once the MMAs above have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1u;
+      const int m0 = (tile % m_tiles) * BM;
+      const int n0 = (tile / m_tiles) * BN;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= epi.n_valid) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), v);
+        tmem_ld_wait();
+        if (row < epi.m_valid) epilogue_chunk(epi, row, col0, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------ SIMT cross-check
+__global__ void gemm_ref_kernel(const __half* __restrict__ a, long long lda, const __half* __restrict__ w, float* c, int M,
+                                int N, int K) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  const __half* ar = a + static_cast<long long>(m) * lda;
+  const __half* wr = w + static_cast<long long>(n) * K;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc = fmaf(__half2float(ar[k]), __half2float(wr[k]), acc);
+  c[static_cast<long long>(m) * N + n] = acc;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  if (!fn) throw Error(2, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  return fn;
+}
+
+}  // namespace
+
+// 2-D fp16 tensor map: inner dimension `cols` (contiguous), `rows` rows of stride `ld` elements, 128B swizzle
+void make_tmap_f16_2d(CUtensorMap* map, const void* ptr, long long cols, long long rows, long long ld, int box_cols,
+                      int box_rows) {
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(2, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+}
+
+void gemm_plan(GemmPlan& p, const __half* a, long long lda, const __half* w, int M, int N, int K, const GemmEpi& epi,
+               int num_sms, int force_bn, int a_wrap) {
+  WISB_REQUIRE(M > 0 && M % BM == 0, "gemm: M must be a positive multiple of 128");
+  WISB_REQUIRE(K > 0 && K % BK == 0, "gemm: K must be a positive multiple of 64");
+  WISB_REQUIRE(N > 0 && N % 32 == 0, "gemm: N must be a positive multiple of 32");
+  WISB_REQUIRE((lda * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+               "gemm: operands must be 16-byte aligned");
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.epi = epi;
+  if (p.epi.m_valid <= 0) p.epi.m_valid = M;
+  if (p.epi.n_valid <= 0) p.epi.n_valid = N;
+  int bn = force_bn;
+  if (bn == 0) {
+    // 256-wide tiles halve the A re-reads; use them when they still give every SM work
+    const int tiles256 = (M / BM) * ((N + 255) / 256);
+    bn = (N % 256 == 0 && tiles256 >= num_sms) ? 256 : 128;
+  }
+  WISB_REQUIRE(bn == 128 || bn == 256, "gemm: BN must be 128 or 256");
+  p.BN = bn;
+  const int tiles = (M / BM) * ((N + bn - 1) / bn);
+  p.grid = tiles < num_sms ? tiles : num_sms;
+  p.a_wrap = a_wrap;
+  if (a_wrap > 0) {
+    WISB_REQUIRE(a_wrap % BK == 0 && lda == a_wrap && K > a_wrap && K - a_wrap <= a_wrap, "gemm: bad a_wrap");
+    make_tmap_f16_2d(&p.map_a, a, a_wrap, M + 1, lda, BK, BM);
+  } else {
+    make_tmap_f16_2d(&p.map_a, a, K, M, lda, BK, BM);
+  }
+  make_tmap_f16_2d(&p.map_b, w, K, N, K, BK, bn);
+}
+
+void gemm_run(const GemmPlan& p, cudaStream_t stream) {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    WISB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::SMEM_BYTES));
+    WISB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::SMEM_BYTES));
+  });
+  if (p.BN == 256) {
+    gemm_tc_kernel<256><<<p.grid, GEMM_THREADS, GemmCfg<256>::SMEM_BYTES, stream>>>(p.map_a, p.map_b, p.M, p.N, p.K, p.a_wrap, p.epi);
+  } else {
+    gemm_tc_kernel<128><<<p.grid, GEMM_THREADS, GemmCfg<128>::SMEM_BYTES, stream>>>(p.map_a, p.map_b, p.M, p.N, p.K, p.a_wrap, p.epi);
+  }
+  WISB_CUDA(cudaGetLastError());
+}
+
+void gemm_ref_run(const __half* a, long long lda, const __half* w, float* c, int M, int N, int K, cudaStream_t stream) {
+  dim3 grid(cdiv(N, 128), M);
+  gemm_ref_kernel<<<grid, 128, 0, stream>>>(a, lda, w, c, M, N, K);
+  WISB_CUDA(cudaGetLastError());
+}
+
+}  // namespace wisb
