@@ -66,10 +66,12 @@ int wisb_generate(wisb_handle* h, const float* mel, int B, const int32_t* prompt
  * lang_ids_out int32 [B, n_langs], probs_out float32 [B, n_langs]. */
 int wisb_detect_language(wisb_handle* h, const float* mel, int B, int32_t* lang_ids_out, float* probs_out);
 
-/* stage timings (ms, CUDA events) of the last wisb_logmel / wisb_generate: [logmel, h2d, encoder, cross_kv, decode,
- * total_generate, decode_steps, kernel_launches] */
-int wisb_get_timing(wisb_handle* h, float* out8);
-/* options: "use_graphs" (default 1), "attn_v_mn_major" (default 1), "attn_ref" (0), "decode_poll" (1) */
+/* stage timings (ms, CUDA events on the launching stream) of the last wisb_logmel / wisb_generate:
+ * [0 logmel, 1 h2d, 2 encoder, 3 cross_kv, 4 decode, 5 total_generate, 6 decode_steps, 7 kernel_launches,
+ *  8 sum of GEMM kernels, 9 attention kernels, 10 LayerNorm kernels, 11 conv1, 12 number of GEMM launches, 13-15 0]
+ * entries 8-12 are filled only with option "profile" = 1 (per-kernel event pairs; leave it off for timed runs). */
+int wisb_get_timing(wisb_handle* h, float* out16);
+/* options: "use_graphs" (default 1), "attn_v_mn_major" (default 1), "attn_ref" (0), "decode_poll" (1), "profile" (0) */
 int wisb_set_option(wisb_handle* h, const char* key, int value);
 
 /* ---- diagnostics used by tests/ (run the product kernels on caller data) ---- */

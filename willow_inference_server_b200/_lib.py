@@ -128,9 +128,10 @@ class Handle:
         check(lib().wisb_set_option(self._h, key.encode(), int(value)))
 
     def timing(self) -> dict:
-        out = np.zeros(8, np.float32)
+        out = np.zeros(16, np.float32)
         check(lib().wisb_get_timing(self._h, ptr(out)))
-        keys = ["logmel_ms", "h2d_ms", "encoder_ms", "cross_kv_ms", "decode_ms", "generate_ms", "decode_steps", "launches"]
+        keys = ["logmel_ms", "h2d_ms", "encoder_ms", "cross_kv_ms", "decode_ms", "generate_ms", "decode_steps", "launches",
+                "gemm_ms", "attn_ms", "ln_ms", "conv1_ms", "gemm_launches"]
         return dict(zip(keys, (float(v) for v in out)))
 
     def logmel(self, pcm, offsets, n_samples, *, to_host=True, keep=False, pcm_on_device=False, pcm_dtype=None, B=None):

@@ -139,8 +139,43 @@ struct wisb_handle {
   std::map<GraphKey, DecGraphs> graphs;
   // timing
   cudaEvent_t ev[8] = {};
-  float timing[8] = {};
+  float timing[16] = {};
   int launches = 0;
+  // optional per-kernel-family profile of the encoder (option "profile"): event pairs on the launching stream
+  int profile = 0;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_cat;  // category of pair i: 0 gemm, 1 attention, 2 layernorm, 3 conv1
+  size_t prof_used = 0;
+  void prof_begin(int cat) {
+    if (!profile) return;
+    if (prof_used + 2 > prof_ev.size()) {
+      cudaEvent_t a, b;
+      WISB_CUDA(cudaEventCreate(&a));
+      WISB_CUDA(cudaEventCreate(&b));
+      prof_ev.push_back(a);
+      prof_ev.push_back(b);
+    }
+    prof_cat.push_back(cat);
+    WISB_CUDA(cudaEventRecord(prof_ev[prof_used], stream));
+  }
+  void prof_end() {
+    if (!profile) return;
+    WISB_CUDA(cudaEventRecord(prof_ev[prof_used + 1], stream));
+    prof_used += 2;
+  }
+  void prof_collect() {  // call after a stream synchronize
+    for (int i = 8; i < 16; ++i) timing[i] = 0.f;
+    if (!profile) return;
+    for (size_t i = 0; i + 1 < prof_used; i += 2) {
+      float ms = 0.f;
+      WISB_CUDA(cudaEventElapsedTime(&ms, prof_ev[i], prof_ev[i + 1]));
+      const int cat = prof_cat[i / 2];
+      timing[8 + cat] += ms;
+      if (cat == 0) timing[12] += 1.f;
+    }
+    prof_used = 0;
+    prof_cat.clear();
+  }
 
   const TensorRef& T(const std::string& name) const {
     auto it = tensors.find(name);
@@ -356,28 +391,50 @@ void run_encoder(wisb_handle* h, int B, int n_layers, bool with_ckv) {
   const int M = B * T_ENC_PAD;
   cudaStream_t s = h->stream;
   ensure_encoder(h, B);
+  h->prof_begin(3);
   conv1_gelu_run(h->mel.p, h->H("enc.conv1.w"), h->F("enc.conv1.b"), h->h1.p, B, d, s);
+  h->prof_end();
+  h->prof_begin(0);
   gemm_run(h->plan_conv2, s);
+  h->prof_end();
   const int nl = (n_layers < 0 || n_layers > dm.n_enc_layers) ? dm.n_enc_layers : n_layers;
   for (int i = 0; i < nl; ++i) {
     const std::string p = "enc." + std::to_string(i) + ".";
     EncLayerPlans& pl = h->enc_plans[i];
+    h->prof_begin(2);
     layernorm_f32_to_f16_run(h->x.p, h->F(p + "ln1.g"), h->F(p + "ln1.b"), h->xn.p, M, d, s);
+    h->prof_end();
+    h->prof_begin(0);
     gemm_run(pl.qkv, s);
+    h->prof_end();
+    h->prof_begin(1);
     if (h->attn_ref)
       enc_attn_ref_run(h->qkv.p, h->ctx.p, B, d, dm.n_heads, s);
     else
       enc_attn_run(h->attn_plan, s);
+    h->prof_end();
+    h->prof_begin(0);
     gemm_run(pl.o, s);
+    h->prof_end();
+    h->prof_begin(2);
     layernorm_f32_to_f16_run(h->x.p, h->F(p + "ln2.g"), h->F(p + "ln2.b"), h->xn.p, M, d, s);
+    h->prof_end();
+    h->prof_begin(0);
     gemm_run(pl.fc1, s);
+    h->prof_end();
+    h->prof_begin(0);
     gemm_run(pl.fc2, s);
+    h->prof_end();
   }
+  h->prof_begin(2);
   layernorm_f32_to_f16_run(h->x.p, h->F("enc.ln_post.g"), h->F("enc.ln_post.b"), h->enc_out.p, M, d, s);
+  h->prof_end();
   h->launches += 2 + 7 * nl + 1;
   if (with_ckv) {
     WISB_CUDA(cudaEventRecord(h->ev[3], s));
+    h->prof_begin(0);
     gemm_run(h->plan_ckv, s);
+    h->prof_end();
     h->launches += 1;
   }
 }
@@ -735,6 +792,7 @@ int wisb_destroy(wisb_handle* h) {
   }
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : h->prof_ev) cudaEventDestroy(e);
   if (h->own_blob && h->blob) cudaFree(h->blob);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -756,14 +814,15 @@ int wisb_set_option(wisb_handle* h, const char* key, int value) {
     else if (k == "attn_v_mn_major") h->attn_v_mn = value;
     else if (k == "attn_ref") h->attn_ref = value;
     else if (k == "decode_poll") h->decode_poll = value < 1 ? 1 : value;
+    else if (k == "profile") h->profile = value;
     else throw Error(1, "unknown option '" + k + "'");
   });
 }
 
-int wisb_get_timing(wisb_handle* h, float* out8) {
+int wisb_get_timing(wisb_handle* h, float* out16) {
   return guarded(h, [&] {
-    WISB_REQUIRE(out8 != nullptr, "out is NULL");
-    memcpy(out8, h->timing, sizeof(h->timing));
+    WISB_REQUIRE(out16 != nullptr, "out is NULL");
+    memcpy(out16, h->timing, sizeof(h->timing));
   });
 }
 
@@ -854,6 +913,7 @@ int wisb_generate(wisb_handle* h, const float* mel, int B, const int32_t* prompt
     WISB_CUDA(cudaEventElapsedTime(&h->timing[5], h->ev[0], h->ev[5]));
     h->timing[6] = static_cast<float>(steps);
     h->timing[7] = static_cast<float>(h->launches);
+    h->prof_collect();
   });
 }
 

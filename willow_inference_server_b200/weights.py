@@ -218,26 +218,42 @@ def synth_state_dict(dims: WhisperDims, seed: int = 0, logit_std: float = 4.0, q
     dec_gain = resid_std / (0.6 * np.sqrt(3.0 * dims.n_dec_layers))
     ss = np.random.SeedSequence(seed)
     counter = [0]
+    deferred = []  # (name-slot, thunk): tensors are drawn in parallel, each from its own counter-derived stream
 
-    def rng():
+    def stream():
         counter[0] += 1
-        return np.random.default_rng(np.random.SeedSequence(entropy=ss.entropy, spawn_key=(counter[0],)))
+        key = counter[0]
+        return lambda: np.random.default_rng(np.random.SeedSequence(entropy=ss.entropy, spawn_key=(key,)))
 
     def h(a):  # round to fp16 grid
         return a.astype(np.float16).astype(np.float32)
 
+    class Lazy:
+        def __init__(self, fn):
+            self.fn = fn
+
+    def normal(shape, scale, half=True, mean=0.0):
+        mk = stream()
+
+        def fn():
+            a = mk().standard_normal(shape, dtype=np.float32) * np.float32(scale)
+            if mean:
+                a = a + np.float32(mean)
+            return h(a) if half else a.astype(np.float32)
+
+        return Lazy(fn)
+
     def lin(n_out, n_in, gain=1.0):
-        return h(rng().standard_normal((n_out, n_in), dtype=np.float32) * np.float32(gain / np.sqrt(n_in)))
+        return normal((n_out, n_in), gain / np.sqrt(n_in))
 
     def vec(n, std=0.02, mean=0.0):
-        return (rng().standard_normal(n, dtype=np.float32) * np.float32(std) + np.float32(mean)).astype(np.float32)
+        return normal(n, std, half=False, mean=mean)
 
     sd = {}
     e = "model.encoder."
-    sd[e + "conv1.weight"] = h(rng().standard_normal((d, dims.n_mels, 3), dtype=np.float32)
-                               * np.float32(1.0 / np.sqrt(3 * dims.n_mels)))
+    sd[e + "conv1.weight"] = normal((d, dims.n_mels, 3), 1.0 / np.sqrt(3 * dims.n_mels))
     sd[e + "conv1.bias"] = vec(d)
-    sd[e + "conv2.weight"] = h(rng().standard_normal((d, d, 3), dtype=np.float32) * np.float32(1.5 / np.sqrt(3 * d)))
+    sd[e + "conv2.weight"] = normal((d, d, 3), 1.5 / np.sqrt(3 * d))
     sd[e + "conv2.bias"] = vec(d)
     sd[e + "embed_positions.weight"] = sinusoids(dims.n_audio_ctx, d)
 
@@ -269,15 +285,8 @@ def synth_state_dict(dims: WhisperDims, seed: int = 0, logit_std: float = 4.0, q
     ln(e + "layer_norm")
 
     dd = "model.decoder."
-    emb = h(rng().standard_normal((dims.n_vocab, d), dtype=np.float32) * np.float32(emb_std))
-    sd[dd + "embed_tokens.weight"] = emb
-    pos = rng().standard_normal((dims.n_text_ctx, d), dtype=np.float32) * np.float32(emb_std)
-    if eot_ramp is not None:
-        p0, slope = eot_ramp
-        u = emb[dims.eot] / np.linalg.norm(emb[dims.eot])
-        ramp = np.maximum(0.0, np.arange(dims.n_text_ctx, dtype=np.float32) - p0) * np.float32(slope)
-        pos = pos + ramp[:, None] * u[None, :]
-    sd[dd + "embed_positions.weight"] = pos.astype(np.float32)
+    sd[dd + "embed_tokens.weight"] = normal((dims.n_vocab, d), emb_std)
+    sd[dd + "embed_positions.weight"] = normal((dims.n_text_ctx, d), emb_std, half=False)
     for i in range(dims.n_dec_layers):
         p = f"{dd}layers.{i}."
         ln(p + "self_attn_layer_norm")
@@ -287,6 +296,20 @@ def synth_state_dict(dims: WhisperDims, seed: int = 0, logit_std: float = 4.0, q
         ln(p + "final_layer_norm")
         mlp(p, dec_gain)
     ln(dd + "layer_norm")
+    # materialise (numpy's Generator releases the GIL: one thread per tensor)
+    from concurrent.futures import ThreadPoolExecutor
+    import os as _os
+
+    names = [k for k, v in sd.items() if isinstance(v, Lazy)]
+    with ThreadPoolExecutor(max_workers=max(1, min(32, (_os.cpu_count() or 1)))) as ex:
+        for k, a in zip(names, ex.map(lambda k: sd[k].fn(), names)):
+            sd[k] = a
+    if eot_ramp is not None:
+        p0, slope = eot_ramp
+        emb = sd[dd + "embed_tokens.weight"]
+        u = emb[dims.eot] / np.linalg.norm(emb[dims.eot])
+        ramp = np.maximum(0.0, np.arange(dims.n_text_ctx, dtype=np.float32) - p0) * np.float32(slope)
+        sd[dd + "embed_positions.weight"] = (sd[dd + "embed_positions.weight"] + ramp[:, None] * u[None, :]).astype(np.float32)
     return sd
 
 
