@@ -62,17 +62,19 @@ def test_forced_logits_match_oracle(pair):
     assert np.abs(got - want).max() <= LOGIT_TOL
 
 
-def _check_tokens(got, res, traces, min_margin):
-    n_checked = 0
+def _explained_mismatches(got, res, traces, thin):
+    """Token lists must be identical unless the oracle itself reports a thin decision margin at the first step where
+    they part ways (fp16 tensor-core activations vs the fp32 oracle can flip a near-tie; everything before it must
+    still agree).  Returns the number of such explained mismatches."""
+    bad = 0
     for g, r, tr in zip(got, res, traces):
         want = r.sequences_ids[0]
-        if min(tr) > min_margin:
-            assert g == want
-            n_checked += 1
-        else:  # ill-posed decision somewhere: the prefix up to the first thin margin must still agree
-            k = next(i for i, m in enumerate(tr) if m <= min_margin)
-            assert g[:k] == want[:k]
-    return n_checked
+        if g == want:
+            continue
+        k = next((i for i, (a, b) in enumerate(zip(g, want)) if a != b), min(len(g), len(want)))
+        assert tr[min(k, len(tr) - 1)] < thin or min(tr[: k + 1]) < thin, (k, g, want, tr)
+        bad += 1
+    return bad
 
 
 @pytest.mark.parametrize("beam", [1, 5, 2])
@@ -86,21 +88,14 @@ def test_generate_matches_oracle(pair, beam):
     m = models.Whisper(None, device="cuda", _handles=[h])
     out = m.generate(models.StorageView.from_array(mel), [PROMPT] * n, beam_size=beam, return_scores=True)
     got = [o.sequences_ids[0] for o in out]
-    if beam == 1:
-        n_ok = _check_tokens(got, res, trace, 4 * LOGIT_TOL)
-        assert n_ok >= n // 2
-    else:
-        # beam search: compare against the oracle; a mismatch is only tolerated if the oracle itself reports a
-        # near-tie between candidates (trace holds the smallest candidate gap per step)
-        for g, r, tr in zip(got, res, trace):
-            if g != r.sequences_ids[0]:
-                assert min(tr) < 2 * LOGIT_TOL / 4, (g, r.sequences_ids[0])
-        agree = sum(g == r.sequences_ids[0] for g, r in zip(got, res))
-        assert agree >= n - 1
+    # greedy: margin = top-1 minus top-2 logit at each step; beam: smallest gap between consecutive candidates
+    bad = _explained_mismatches(got, res, trace, 2 * LOGIT_TOL)
+    assert bad <= 1, f"{bad} of {n} transcripts differ from the oracle"
     for o, r in zip(out, res):
         if o.sequences_ids[0] == r.sequences_ids[0] and beam > 1:
             assert abs(o.scores[0] - r.scores[0]) < 5e-2
         assert dims.eot not in o.sequences_ids[0]
+        assert not set(o.sequences_ids[0]) & set(dims.suppress_ids)
 
 
 def test_graphs_and_eager_agree(pair):

@@ -5,7 +5,7 @@
 
 namespace wisb {
 
-constexpr int DEC_MAX_ROWS = 16;   // rows (utterances x beams) one decoder pass handles
+constexpr int DEC_MAX_ROWS = 8;    // rows (utterances x beams) one decoder pass handles
 constexpr int MAX_BEAM = 8;
 constexpr int MAX_CAND = 2 * MAX_BEAM;
 constexpr int TOPK_CHUNKS = 32;
@@ -68,6 +68,8 @@ struct SearchArgs {
   float length_penalty = 1.f;
   // workspaces / state (device)
   float* row_lse = nullptr;       // [R]
+  float* part_max = nullptr;      // [R][TOPK_CHUNKS] chunk max of the processed logits
+  float* part_sum = nullptr;      // [R][TOPK_CHUNKS] chunk sum exp(logit - chunk max)
   float* cum = nullptr;           // [R] cumulative log-prob of the alive beams
   unsigned long long* part = nullptr;  // [R][TOPK_CHUNKS][MAX_CAND] packed (score, ~index)
   float* cand_score = nullptr;    // [n_utt][MAX_CAND]

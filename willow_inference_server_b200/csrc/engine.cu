@@ -129,7 +129,7 @@ struct wisb_handle {
   DevBuf<__half> kcache, vcache;  // [L][16][448][d]
   DevBuf<uint8_t> mask_base, mask_cur;
   std::vector<int> mask_extra;
-  DevBuf<float> row_lse, cum, cand_score, best_score, lang_probs;
+  DevBuf<float> row_lse, cum, cand_score, best_score, lang_probs, part_max, part_sum;
   DevBuf<unsigned long long> part;
   DevBuf<int> cand_idx, tokens, seq0, seq1, ind0, ind1, flip, done, n_hyp, best_len, best_tokens, prompt_dev, lang_ids;
   DevBuf<DecState> st;
@@ -284,6 +284,7 @@ void finish_create(wisb_handle* h) {
   h->kcache.ensure(cache, true);
   h->vcache.ensure(cache, true);
   h->row_lse.ensure(R); h->cum.ensure(R);
+  h->part_max.ensure(R * TOPK_CHUNKS); h->part_sum.ensure(R * TOPK_CHUNKS);
   h->part.ensure(R * TOPK_CHUNKS * MAX_CAND);
   h->cand_score.ensure(R * MAX_CAND); h->cand_idx.ensure(R * MAX_CAND);
   h->tokens.ensure(R);
@@ -472,6 +473,8 @@ SearchArgs make_search_args(wisb_handle* h, const DecodeCfg& c) {
   a.prompt_len = c.prompt_len;
   a.length_penalty = c.lp;
   a.row_lse = h->row_lse.p;
+  a.part_max = h->part_max.p;
+  a.part_sum = h->part_sum.p;
   a.cum = h->cum.p;
   a.part = h->part.p;
   a.cand_score = h->cand_score.p;
@@ -626,8 +629,8 @@ int decode_pass(wisb_handle* h, const DecodeCfg& c, const int32_t* prompts, int3
       if (g) WISB_CUDA(cudaGraphLaunch(g->prefill, s)); else enqueue_prefill(h, c);
       ++steps;
     }
-    const int per_step = 1 + 8 * h->dims.n_dec_layers + 1 + 5;
-    h->launches += (c.prompt_len - 1) * (per_step - 5);
+    const int per_step = 1 + 8 * h->dims.n_dec_layers + 1 + 4;
+    h->launches += (c.prompt_len - 1) * (per_step - 4);
     volatile int* flag = h->pin_i.p;
     *flag = 0;
     for (int gs = 0; gs < c.max_new; ++gs) {

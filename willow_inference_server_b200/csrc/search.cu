@@ -35,34 +35,6 @@ __device__ __forceinline__ float masked_logit(const SearchArgs& a, const float* 
   return row[v];
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// per row: lse = log sum exp of the processed logits
-__global__ void __launch_bounds__(1024) row_lse_kernel(const SearchArgs a) {
-  __shared__ float red[32];
-  const int r = blockIdx.x;
-  const float* row = a.logits + static_cast<long long>(r) * a.ldl;
-  const bool first = a.st->gen_step == 0;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float mx = -INFINITY;
-  for (int v = tid; v < a.n_vocab; v += blockDim.x) mx = fmaxf(mx, masked_logit(a, row, v, first));
-  mx = warp_max(mx);
-  if (lane == 0) red[warp] = mx;
-  __syncthreads();
-  mx = red[0];
-  for (int w = 1; w < (blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
-  __syncthreads();
-  float s = 0.f;
-  for (int v = tid; v < a.n_vocab; v += blockDim.x) s += __expf(masked_logit(a, row, v, first) - mx);
-  s = warp_sum(s);
-  if (lane == 0) red[warp] = s;
-  __syncthreads();
-  if (tid == 0) {
-    float t = 0.f;
-    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
-    a.row_lse[r] = mx + logf(t);
-  }
-}
-
 // block-wide selection of the `n_cand` largest keys among each thread's private keys[0..cnt)
 template <int PER>
 __device__ void block_select(unsigned long long (&keys)[PER], int n_cand, unsigned long long* out,
@@ -103,31 +75,50 @@ constexpr int TK_THREADS = 256;
 constexpr int TK_PER = 8;  // 256 * 8 = 2048 >= ceil(51865 / 32) = 1621
 
 __global__ void __launch_bounds__(TK_THREADS) topk_partial_kernel(const SearchArgs a) {
+  // Within one row the ranking by processed logit equals the ranking by score, so the per-chunk stage needs no
+  // log-sum-exp: it emits the chunk's top-n_cand logits plus (max, sum exp) partials; the merge stage turns them into
+  // the row's lse and into scores.  (This replaced a separate two-pass lse kernel: 55 us -> 0.)
   __shared__ unsigned long long s_red[32];
+  __shared__ float s_f[32];
   const int chunk = blockIdx.x, r = blockIdx.y;
-  const int u = r / a.beam, k = r - u * a.beam;
-  const int gen = a.st->gen_step;
-  const bool first = gen == 0;
+  const bool first = a.st->gen_step == 0;
   const float* row = a.logits + static_cast<long long>(r) * a.ldl;
   const int per_chunk = (a.n_vocab + TOPK_CHUNKS - 1) / TOPK_CHUNKS;
   const int v0 = chunk * per_chunk;
   const int v1 = min(a.n_vocab, v0 + per_chunk);
-  const float norm = (a.length_penalty != 0.f) ? powf(static_cast<float>(gen + 1), a.length_penalty) : 1.f;
-  const float lse = a.row_lse[r];
-  const float cum = a.cum[r];
-  const bool live = !(first && k > 0);  // at the first step every beam holds the same prefix: only beam 0 counts
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned long long keys[TK_PER];
+  float lg[TK_PER];
+  float mx = -INFINITY;
 #pragma unroll
   for (int i = 0; i < TK_PER; ++i) {
-    const int v = v0 + threadIdx.x + i * TK_THREADS;
+    const int v = v0 + tid + i * TK_THREADS;
     keys[i] = 0ull;
-    if (live && v < v1) {
-      const float lg = masked_logit(a, row, v, first);
-      if (lg != -INFINITY) {
-        const float sc = ((lg - lse) + cum) / norm;
-        keys[i] = pack_key(sc, static_cast<unsigned>(k * a.n_vocab + v));
-      }
+    lg[i] = -INFINITY;
+    if (v < v1) {
+      lg[i] = masked_logit(a, row, v, first);
+      if (lg[i] != -INFINITY) keys[i] = pack_key(lg[i], static_cast<unsigned>(v));
+      mx = fmaxf(mx, lg[i]);
     }
+  }
+  mx = warp_max(mx);
+  if (lane == 0) s_f[warp] = mx;
+  __syncthreads();
+  mx = s_f[0];
+  for (int w = 1; w < TK_THREADS / 32; ++w) mx = fmaxf(mx, s_f[w]);
+  __syncthreads();
+  float se = 0.f;
+#pragma unroll
+  for (int i = 0; i < TK_PER; ++i)
+    if (lg[i] != -INFINITY) se += __expf(lg[i] - mx);
+  se = warp_sum(se);
+  if (lane == 0) s_f[warp] = se;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int w = 0; w < TK_THREADS / 32; ++w) t += s_f[w];
+    a.part_max[r * TOPK_CHUNKS + chunk] = mx;
+    a.part_sum[r * TOPK_CHUNKS + chunk] = t;
   }
   block_select<TK_PER>(keys, a.n_cand, a.part + (static_cast<long long>(r) * TOPK_CHUNKS + chunk) * MAX_CAND, s_red);
 }
@@ -138,7 +129,24 @@ constexpr int TM_PER = (MAX_BEAM * TOPK_CHUNKS * MAX_CAND + TK_THREADS - 1) / TK
 __global__ void __launch_bounds__(TK_THREADS) topk_merge_kernel(const SearchArgs a) {
   __shared__ unsigned long long s_red[32];
   __shared__ unsigned long long s_out[MAX_CAND];
+  __shared__ float s_lse[MAX_BEAM];
   const int u = blockIdx.x;
+  const int gen = a.st->gen_step;
+  const bool first = gen == 0;
+  const float norm = (a.length_penalty != 0.f) ? powf(static_cast<float>(gen + 1), a.length_penalty) : 1.f;
+  if (threadIdx.x < a.beam) {  // row log-sum-exp from the chunk partials
+    const int r = u * a.beam + threadIdx.x;
+    float mx = -INFINITY;
+    for (int c = 0; c < TOPK_CHUNKS; ++c) mx = fmaxf(mx, a.part_max[r * TOPK_CHUNKS + c]);
+    float t = 0.f;
+    for (int c = 0; c < TOPK_CHUNKS; ++c) {
+      const float pm = a.part_max[r * TOPK_CHUNKS + c];
+      if (pm != -INFINITY) t += a.part_sum[r * TOPK_CHUNKS + c] * __expf(pm - mx);
+    }
+    s_lse[threadIdx.x] = mx + logf(t);
+    a.row_lse[r] = s_lse[threadIdx.x];
+  }
+  __syncthreads();
   const int total = a.beam * TOPK_CHUNKS * a.n_cand;
   unsigned long long keys[TM_PER];
 #pragma unroll
@@ -147,8 +155,16 @@ __global__ void __launch_bounds__(TK_THREADS) topk_merge_kernel(const SearchArgs
     keys[i] = 0ull;
     if (j < total) {
       const int c = j % a.n_cand;
-      const int rc = j / a.n_cand;  // (beam row, chunk)
-      keys[i] = a.part[(static_cast<long long>(u * a.beam) * TOPK_CHUNKS + rc) * MAX_CAND + c];
+      const int rc = j / a.n_cand;       // (beam row, chunk)
+      const int k = rc / TOPK_CHUNKS;    // beam index
+      const unsigned long long pk = a.part[(static_cast<long long>(u * a.beam) * TOPK_CHUNKS + rc) * MAX_CAND + c];
+      // at the first step every beam holds the same prefix: only beam 0 counts
+      if (pk != 0ull && !(first && k > 0)) {
+        const float lg = ord2f(static_cast<unsigned>(pk >> 32));
+        const unsigned v = ~static_cast<unsigned>(pk & 0xffffffffull);
+        const float sc = ((lg - s_lse[k]) + a.cum[u * a.beam + k]) / norm;
+        keys[i] = pack_key(sc, static_cast<unsigned>(k * a.n_vocab) + v);
+      }
     }
   }
   block_select<TM_PER>(keys, a.n_cand, s_out, s_red);
@@ -322,7 +338,6 @@ void search_step_run(const SearchArgs& a, cudaStream_t stream) {
   const int R = a.n_utt * a.beam;
   WISB_REQUIRE(a.beam >= 1 && a.beam <= MAX_BEAM && a.n_cand <= MAX_CAND, "search: beam_size must be in [1, 8]");
   WISB_REQUIRE((a.n_vocab + TOPK_CHUNKS - 1) / TOPK_CHUNKS <= TK_THREADS * TK_PER, "search: vocabulary too large");
-  row_lse_kernel<<<R, 1024, 0, stream>>>(a);
   topk_partial_kernel<<<dim3(TOPK_CHUNKS, R), TK_THREADS, 0, stream>>>(a);
   topk_merge_kernel<<<a.n_utt, TK_THREADS, 0, stream>>>(a);
   search_bookkeeping_kernel<<<a.n_utt, 32, 0, stream>>>(a);
