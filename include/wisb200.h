@@ -71,12 +71,15 @@ int wisb_detect_language(wisb_handle* h, const float* mel, int B, int32_t* lang_
  *  8 sum of GEMM kernels, 9 attention kernels, 10 LayerNorm kernels, 11 conv1, 12 number of GEMM launches, 13-15 0]
  * entries 8-12 are filled only with option "profile" = 1 (per-kernel event pairs; leave it off for timed runs). */
 int wisb_get_timing(wisb_handle* h, float* out16);
-/* options: "use_graphs" (default 1), "attn_v_mn_major" (default 1), "attn_ref" (0), "decode_poll" (1), "profile" (0) */
+/* options: "use_graphs" (default 1), "attn_v_mn_major" (default 1), "attn_ref" (0), "decode_poll" (1), "profile" (0),
+ * "decoder_mega" (1: persistent decoder-pass kernel; 0: the per-op kernel chain kept as a cross-check) */
 int wisb_set_option(wisb_handle* h, const char* key, int value);
 
 /* ---- diagnostics used by tests/ (run the product kernels on caller data) ---- */
 /* C[M,N] (float32) = A[M,K] . W[N,K]^T with fp16 inputs given as raw uint16; impl 0 = tcgen05 kernel, 1 = SIMT check */
 int wisb_debug_gemm(wisb_handle* h, const uint16_t* a, const uint16_t* w, float* c, int M, int N, int K, int impl, int bn);
+/* per-phase %globaltimer stamps of the last persistent decoder pass (option "mega_trace" = 1): n <= 2048 values */
+int wisb_debug_read_trace(wisb_handle* h, unsigned long long* out, int n);
 /* encoder output after the final LayerNorm, float32 [B,1500,d_model]; n_layers < 0 = all */
 int wisb_debug_encode(wisb_handle* h, const float* mel, int B, float* enc_out, int n_layers);
 /* teacher-forced raw decoder logits (no processors) for utterance 0: float32 [n_tokens, n_vocab] */

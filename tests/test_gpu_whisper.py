@@ -108,6 +108,21 @@ def test_graphs_and_eager_agree(pair):
     assert a == b
 
 
+def test_persistent_pass_kernel_vs_per_op_chain(pair):
+    # the persistent decoder-pass kernel and the per-op kernel chain are two implementations of the same arithmetic
+    dims, oracle, h = pair
+    mel = mel_inputs(4)[:2]
+    toks = PROMPT + [100, 2000, 30000, 41000, 12]
+    a = h.debug_forced_logits(mel[:1], toks)
+    ids_a, _ = h.generate(mel, [PROMPT] * 2, beam_size=5)
+    h.set_option("decoder_mega", 0)
+    b = h.debug_forced_logits(mel[:1], toks)
+    ids_b, _ = h.generate(mel, [PROMPT] * 2, beam_size=5)
+    h.set_option("decoder_mega", 1)
+    assert np.abs(a - b).max() < 2e-3
+    assert ids_a == ids_b
+
+
 def test_max_length_and_suppress(pair):
     dims, oracle, h = pair
     mel = mel_inputs(4)[:1]

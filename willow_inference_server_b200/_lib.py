@@ -36,6 +36,7 @@ _SIGS = {
     "wisb_get_timing": (C.c_int, [C.c_void_p, C.c_void_p]),
     "wisb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "wisb_debug_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "wisb_debug_read_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "wisb_debug_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "wisb_debug_forced_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
 }
@@ -193,6 +194,11 @@ class Handle:
         c = np.zeros((M, N), np.float32)
         check(lib().wisb_debug_gemm(self._h, ptr(a16), ptr(w16), ptr(c), M, N, K, impl, bn))
         return c
+
+    def debug_read_trace(self, n: int = 600) -> np.ndarray:
+        out = np.zeros(n, np.uint64)
+        check(lib().wisb_debug_read_trace(self._h, ptr(out), n))
+        return out
 
     def debug_encode(self, mel: np.ndarray, n_layers: int = -1) -> np.ndarray:
         mel = np.ascontiguousarray(mel, np.float32)

@@ -91,6 +91,51 @@ void prefill_advance_run(int* tokens, const int* prompt /*[n_utt][prompt_len]*/,
                          DecState* st, cudaStream_t stream);
 void search_init_run(const SearchArgs& a, const int* prompt, cudaStream_t stream);
 
+// ------------------------------------------------------------------ persistent decoder pass (decoder_mega.cu)
+struct MegaGemv {
+  const __half* w = nullptr;     // [N, K] fp16; K > 1536: chunk-major [chunk][N][K/chunks] (mega_chunk_major)
+  const float* bias = nullptr;
+  const float* ln_g = nullptr;   // LayerNorm on x when non-null (K <= 1536)
+  const float* ln_b = nullptr;
+  const float* x = nullptr;      // [R, K] fp32 activations
+  float* out = nullptr;
+  long long ldo = 0;
+  int N = 0, K = 0, epi = GV_STORE;
+};
+struct MegaLayer {
+  MegaGemv qkv, o, cq, co, fc1, fc2;
+  const __half* ck = nullptr;    // cross K of this layer for the utterances of the pass: [n_utt][H][1536][64]
+  const __half* cv = nullptr;
+  __half* kcache = nullptr;      // self-attention cache of this layer: [slots][t_max][d]
+  __half* vcache = nullptr;
+};
+struct MegaArgs {
+  const MegaLayer* layers = nullptr;  // device array [n_layers]
+  int n_layers = 0;
+  MegaGemv vocab;
+  int with_logits = 0;
+  int R = 0, d = 0, H = 0, n_utt = 0, beam = 0, t_max = 0;
+  const int* tokens = nullptr;
+  const __half* tok_emb = nullptr;
+  const float* pos_emb = nullptr;
+  float* x = nullptr;      // [R, d] residual stream
+  float* q = nullptr;      // [R, d]
+  float* ctx = nullptr;    // [R, d]
+  const int* indir0 = nullptr;
+  const int* indir1 = nullptr;
+  const int* flip = nullptr;
+  const DecState* st = nullptr;
+  float* cross_part = nullptr;   // [n_utt][H][S<=16][MAX_BEAM][68] (64 acc, m, l, pad)
+  unsigned* cross_count = nullptr;  // [n_utt * H] arrival counters of the key splits (zero between layers)
+  unsigned* flags = nullptr;     // grid-barrier epoch flags, one 128-byte line per CTA
+  unsigned* epoch_base = nullptr;
+  unsigned long long* trace = nullptr;  // optional: [2*k] = time phase k starts, [2*k+1] = time CTA 0 reached barrier k
+};
+size_t mega_flags_words();
+int mega_k_chunks(int K);
+void mega_chunk_major(const __half* src, __half* dst, int N, int K, cudaStream_t stream);
+void dec_pass_run(const MegaArgs& a, int num_sms, cudaStream_t stream);
+
 // language detection head: softmax over lang ids of the logits of row u*beam (one step on <|startoftranscript|>)
 void lang_probs_run(const float* logits, long long ldl, const int* lang_ids, int n_lang, int n_utt, int row_stride,
                     float* probs /*[n_utt][n_lang]*/, cudaStream_t stream);

@@ -1,0 +1,747 @@
+// Persistent decoder-pass kernel ("megakernel"): one cooperative launch runs a whole decoder forward pass
+// (embedding, L x {LN+QKV, self-attention, out-proj, LN+cross-Q, cross-attention, out-proj, LN+fc1+GELU, fc2},
+// final LN + vocabulary projection) for <= 8 rows, instead of ~260 dependent kernel launches.
+//
+// Why: at <= 8 rows the pass is bound by streaming 1.8 GB of fp16 decoder weights, but a chain
+// of per-op kernels exposes launch + HBM latency ~260 times per pass (measured: 2.1 ms / pass = 7 % of the HBM
+// roofline even with PDL).  Here
+//   * one CTA per SM, every CTA owns a fixed column slice of every weight matrix;
+//   * a dedicated producer thread per CTA walks the (static) list of weight chunks of ALL phases and streams them into a
+//     5-stage shared-memory ring with cp.async.bulk (TMA) + mbarrier complete_tx -- it never waits for activations, so
+//     the HBM stream keeps running across phase boundaries (the ring holds several phases of look-ahead);
+//   * consumer warps wait only on (a) the ring and (b) a flag-based grid barrier between phases (per-CTA epoch flags,
+//     no atomics), and read activations with L1-bypassing loads;
+//   * activations stay fp32; LayerNorm (single-pass sum / sum-of-squares statistics in fp32) is applied in registers while staging x.
+// Mapping inside a GEMV phase: thread = one 16-byte K-slice (8 elements) of the CTA's columns; it keeps x[r][8] of all
+// rows in registers and streams the CTA's <= 12 columns through them (weights from the ring), then a transposing warp
+// reduction + one shared-memory hop produce the outputs.
+//
+// Reference semantics: decoder step of ctranslate2.models.Whisper.generate (/root/reference/main.py:687-692);
+// architecture [HF] modeling_whisper.py:417-508, :650-700, :966-971.
+#include <cooperative_groups.h>
+
+#include "decoder.cuh"
+#include "ptx.cuh"
+
+namespace wisb {
+
+namespace {
+
+constexpr int MG_CONS_WARPS = 7;                        // consumer warps
+constexpr int MG_CONS = MG_CONS_WARPS * 32;             // 320 consumer threads
+constexpr int MG_THREADS = MG_CONS + 32;                // + producer warp (lane 0 only)
+constexpr int MG_KC_MAX = 1536;
+constexpr int MG_STAGE_BYTES = 12 * MG_KC_MAX * 2;      // 36864: up to 12 weight-row chunks (or 288 keys of K / V)
+constexpr int MG_NSTAGE = 5;
+constexpr int MG_CA_KEYS_MAX = MG_STAGE_BYTES / 128;    // 288 keys per K (or V) chunk
+constexpr int MG_SCRATCH = 28672;                       // self-attention probabilities / cross-attention merge
+constexpr int MG_SMEM = MG_NSTAGE * MG_STAGE_BYTES + 1024 + 2 * MG_CONS_WARPS * 32 * 4 + 4096 + MG_SCRATCH;
+// columns a thread accumulates per unit: the transposing reduction handles GP * NR <= 32 values
+__host__ __device__ constexpr int mg_gp(int nr) { return 32 / nr < 6 ? 32 / nr : 6; }
+
+__device__ __forceinline__ float ldcg_f(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ float4 ldcg_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(MG_CONS) : "memory"); }
+
+// in: lane l holds v[0..31]; out: v[0] of lane l = sum over all lanes of their v[l]
+__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < n / 2) {
+        const float send = up ? v[i] : v[i + n / 2];
+        const float keep = up ? v[i + n / 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+  }
+  return v[0];
+}
+
+struct Ring {
+  uint32_t full0, empty0, data0;  // shared-memory addresses
+  uint8_t* data;
+  unsigned unit;                  // running unit counter (same sequence in producer and consumers)
+  __device__ __forceinline__ uint32_t full(int s) const { return full0 + 8u * s; }
+  __device__ __forceinline__ uint32_t empty(int s) const { return empty0 + 8u * s; }
+};
+
+// column slice of a GEMV phase owned by this CTA
+__device__ __forceinline__ void cta_cols(int N, int& lo, int& hi) {
+  const int per = (N + gridDim.x - 1) / gridDim.x;
+  lo = blockIdx.x * per;
+  hi = min(N, lo + per);
+  if (lo > hi) lo = hi;
+}
+__device__ __forceinline__ void k_split(int K, int& n_chunks, int& kc) {
+  n_chunks = (K + MG_KC_MAX - 1) / MG_KC_MAX;
+  while (K % (8 * n_chunks) != 0) ++n_chunks;
+  kc = K / n_chunks;
+}
+// thread parts: `wpp` warps cover the kc/8 K-slices once; with <= 5 warps per part two parts split the columns
+__device__ __forceinline__ void part_geom(int kc, int& wpp, int& n_parts) {
+  wpp = (kc / 8 + 31) / 32;
+  n_parts = (2 * wpp <= MG_CONS_WARPS) ? 2 : 1;
+}
+
+// ------------------------------------------------------------------ producer side
+__device__ __noinline__ void produce_gemv(Ring& rg, const MegaGemv& g, int gp) {
+  int lo, hi, n_chunks, kc, wpp, n_parts;
+  cta_cols(g.N, lo, hi);
+  k_split(g.K, n_chunks, kc);
+  part_geom(kc, wpp, n_parts);
+  const int G = gp * n_parts;
+  for (int g0 = lo; g0 < hi; g0 += G) {
+    const int nc = min(G, hi - g0);
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int st = rg.unit % MG_NSTAGE;
+      mbar_wait(rg.empty(st), ((rg.unit / MG_NSTAGE) & 1u) ^ 1u);
+      // one TMA request per unit: rows g0..g0+nc of a K-chunk are contiguous (multi-chunk matrices are stored
+      // chunk-major [chunk][N][kc] by the engine at load time).  Many small copies (one per 2.5 KB row) were bound by
+      // the per-request rate of the copy engine (~0.6 us each, 590 GB/s aggregate).
+      mbar_arrive_expect_tx(rg.full(st), static_cast<uint32_t>(nc * kc * 2));
+      bulk_load_1d(rg.data0 + st * MG_STAGE_BYTES, g.w + (static_cast<long long>(ch) * g.N + g0) * kc,
+                   static_cast<uint32_t>(nc * kc * 2), rg.full(st));
+      ++rg.unit;
+    }
+  }
+}
+
+struct CrossGeom {
+  int S, KS, n_tasks;
+};
+__device__ __forceinline__ CrossGeom cross_geom(int n_utt, int H) {
+  CrossGeom c;
+  int s = gridDim.x / (n_utt * H);
+  const int smin = (T_ENC + MG_CA_KEYS_MAX - 1) / MG_CA_KEYS_MAX;  // 6
+  if (s < smin) s = smin;
+  if (s > 16) s = 16;
+  c.S = s;
+  c.KS = ((T_ENC + s - 1) / s + 7) & ~7;
+  c.n_tasks = n_utt * H * s;
+  return c;
+}
+
+__device__ __noinline__ void produce_cross(Ring& rg, const MegaArgs& A, const MegaLayer& ly) {
+  const CrossGeom cg = cross_geom(A.n_utt, A.H);
+  for (int task = blockIdx.x; task < cg.n_tasks; task += gridDim.x) {
+    const int split = task % cg.S, uh = task / cg.S;
+    const int t0 = split * cg.KS;
+    const int nk = min(cg.KS, T_ENC_PAD - t0);  // buffer has 1536 rows; keys >= 1500 are masked by the consumer
+    const long long off = (static_cast<long long>(uh) * T_ENC_PAD + t0) * HEAD_DIM;
+    for (int kv = 0; kv < 2; ++kv) {
+      const int st = rg.unit % MG_NSTAGE;
+      mbar_wait(rg.empty(st), ((rg.unit / MG_NSTAGE) & 1u) ^ 1u);
+      mbar_arrive_expect_tx(rg.full(st), static_cast<uint32_t>(nk * HEAD_DIM * 2));
+      bulk_load_1d(rg.data0 + st * MG_STAGE_BYTES, (kv == 0 ? ly.ck : ly.cv) + off, static_cast<uint32_t>(nk * HEAD_DIM * 2),
+                   rg.full(st));
+      ++rg.unit;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ grid barrier (consumers only)
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// fine-grained event trace of CTA 0 / thread 0 (debug): trace[1024 + 2 i] = event id, [.. + 1] = time
+__device__ __forceinline__ void trace_ev(const MegaArgs& A, int ctid, int* s_tr, int id) {
+  if (A.trace != nullptr && blockIdx.x == 0 && ctid == 0) {
+    const int i = (*s_tr)++;
+    if (i < 500) {
+      A.trace[1024 + 2 * i] = static_cast<unsigned long long>(id);
+      A.trace[1024 + 2 * i + 1] = globaltimer_ns();
+    }
+  }
+}
+
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Flag barrier: bar.sync orders the CTA's writes before thread 0's release store (cumulativity); every CTA publishes its
+// epoch in its own 128-byte line and thread i polls CTA i's line with acquire loads -- no atomics, no all-thread fences.
+__device__ __forceinline__ void grid_barrier(const MegaArgs& A, unsigned& epoch, int ctid, unsigned epoch0) {
+  if (A.trace != nullptr && blockIdx.x == 0 && ctid == 0) A.trace[2 * (epoch - epoch0) + 1] = globaltimer_ns();
+  cons_sync();
+  ++epoch;
+  if (ctid == 0) st_release_gpu(A.flags + blockIdx.x * 32, epoch);
+  if (ctid < static_cast<int>(gridDim.x)) {
+    const unsigned* f = A.flags + ctid * 32;
+    while (static_cast<int>(ld_acquire_gpu(f) - epoch) < 0) {
+    }
+  }
+  cons_sync();
+  if (A.trace != nullptr && blockIdx.x == 0 && ctid == 0) A.trace[2 * (epoch - epoch0)] = globaltimer_ns();
+}
+
+// ------------------------------------------------------------------ consumer: one GEMV phase
+template <int NR>
+__device__ __noinline__ void consume_gemv(Ring& rg, const MegaArgs& A, const MegaGemv& g, const MegaLayer* ly, int ctid,
+                                          float* s_red, float* s_stat, float* s_comb) {
+  const int lane = ctid & 31, warp = ctid >> 5;
+  const int R = A.R;
+  int lo, hi, n_chunks, kc;
+  cta_cols(g.N, lo, hi);
+  k_split(g.K, n_chunks, kc);
+  constexpr int MG_GP = mg_gp(NR);
+  const int n_kvec = kc / 8;
+  int wpp, n_parts;
+  part_geom(kc, wpp, n_parts);
+  const int MG_G = MG_GP * n_parts;
+  const int part = warp / wpp;
+  const int kv = (warp - part * wpp) * 32 + lane;
+  const bool active = part < n_parts && kv < n_kvec;
+  const bool ln = g.ln_g != nullptr;
+
+  int* s_tr = reinterpret_cast<int*>(s_stat + 1001);
+  trace_ev(A, ctid, s_tr, 1);
+  float* s_bias = s_stat + 256;   // [<=512] this CTA's bias slice, prefetched while x is in flight
+  float* s_xown = s_stat + 768;   // [8][16]  residual-stream columns owned by this CTA (kept across phases)
+  const int ncols = hi - lo;
+  const bool bias_smem = g.bias != nullptr && ncols <= 512;
+  if (bias_smem)
+    for (int i = ctid; i < ncols; i += MG_CONS) s_bias[i] = __ldg(g.bias + lo + i);
+  float acc[MG_GP][NR];
+  float xv[NR][8], xn[NR][8];
+  int grp_idx = 0;
+  auto load_x = [&](float (&dst)[NR][8], int ch) {
+    const int k = ch * kc + kv * 8;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dst[r][i] = 0.f;
+      if (active && r < R) {
+        const float4 x0 = ldcg_f4(g.x + static_cast<long long>(r) * g.K + k), x1 = ldcg_f4(g.x + static_cast<long long>(r) * g.K + k + 4);
+        dst[r][0] = x0.x; dst[r][1] = x0.y; dst[r][2] = x0.z; dst[r][3] = x0.w;
+        dst[r][4] = x1.x; dst[r][5] = x1.y; dst[r][6] = x1.z; dst[r][7] = x1.w;
+      }
+    }
+  };
+  for (int g0 = lo; g0 < hi; g0 += MG_G) {
+    const int nc = min(MG_G, hi - g0);
+#pragma unroll
+    for (int j = 0; j < MG_GP; ++j)
+#pragma unroll
+      for (int r = 0; r < NR; ++r) acc[j][r] = 0.f;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      // ---- stage x[r][8] for this thread's K-slice (only when the slice changes: first group, or multi-chunk K);
+      //      with a multi-chunk K the next chunk's loads are issued before this chunk's math (software prefetch)
+      if (g0 == lo || n_chunks > 1) {
+        const int k = ch * kc + kv * 8;
+        if (n_chunks == 1 || ch == 0) {
+          load_x(xv, ch);
+        } else {
+#pragma unroll
+          for (int r = 0; r < NR; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xv[r][i] = xn[r][i];
+        }
+        if (n_chunks > 1) load_x(xn, (ch + 1) % n_chunks);
+        if (ln) {  // LayerNorm over the CTA (K <= 1536: single chunk): one reduction round for sum and sum of squares
+          float gg[8], bb[8];
+          if (active) {  // parameter loads in flight while the statistics are reduced
+            const float4 g0v = __ldg(reinterpret_cast<const float4*>(g.ln_g + k)), g1v = __ldg(reinterpret_cast<const float4*>(g.ln_g + k + 4));
+            const float4 b0v = __ldg(reinterpret_cast<const float4*>(g.ln_b + k)), b1v = __ldg(reinterpret_cast<const float4*>(g.ln_b + k + 4));
+            gg[0] = g0v.x; gg[1] = g0v.y; gg[2] = g0v.z; gg[3] = g0v.w; gg[4] = g1v.x; gg[5] = g1v.y; gg[6] = g1v.z; gg[7] = g1v.w;
+            bb[0] = b0v.x; bb[1] = b0v.y; bb[2] = b0v.z; bb[3] = b0v.w; bb[4] = b1v.x; bb[5] = b1v.y; bb[6] = b1v.z; bb[7] = b1v.w;
+          }
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            float s1 = 0.f, s2 = 0.f;
+            if (part == 0)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                s1 += xv[r][i];
+                s2 = fmaf(xv[r][i], xv[r][i], s2);
+              }
+            s1 = warp_sum(s1);
+            s2 = warp_sum(s2);
+            if (lane == 0) {
+              s_stat[warp * 16 + r] = s1;
+              s_stat[warp * 16 + 8 + r] = s2;
+            }
+          }
+          cons_sync();
+          if (active) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+              float t1 = 0.f, t2 = 0.f;
+              for (int w = 0; w < wpp; ++w) {
+                t1 += s_stat[w * 16 + r];
+                t2 += s_stat[w * 16 + 8 + r];
+              }
+              const float mean = t1 / g.K;
+              const float rstd = rsqrtf(fmaxf(t2 / g.K - mean * mean, 0.f) + 1e-5f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) xv[r][i] = (xv[r][i] - mean) * rstd * gg[i] + bb[i];
+            }
+          }
+          cons_sync();  // s_stat reusable
+        }
+      }
+      // ---- weights of this unit from the ring
+      trace_ev(A, ctid, s_tr, 2);
+      const int st = rg.unit % MG_NSTAGE;
+      mbar_wait(rg.full(st), (rg.unit / MG_NSTAGE) & 1u);
+      trace_ev(A, ctid, s_tr, 3);
+      if (active) {
+        const uint8_t* stage = rg.data + st * MG_STAGE_BYTES;
+#pragma unroll
+        for (int j = 0; j < MG_GP; ++j) {
+          const int cj = part + n_parts * j;
+          if (cj < nc) {
+            const uint4 u4 = *reinterpret_cast<const uint4*>(stage + cj * kc * 2 + kv * 16);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&u4);
+            float wf[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __half22float2(h2[i]);
+              wf[2 * i] = f.x;
+              wf[2 * i + 1] = f.y;
+            }
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[j][r] = fmaf(xv[r][i], wf[i], acc[j][r]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rg.empty(st));
+      ++rg.unit;
+    }
+    // ---- group done: reduce over the K-slices (lanes, then the warps of the part) and write the outputs
+    trace_ev(A, ctid, s_tr, 4);
+    float red[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) red[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < MG_GP; ++j)
+#pragma unroll
+      for (int r = 0; r < NR; ++r) red[j * NR + r] = acc[j][r];
+    const float tot = warp_transpose_reduce32(red, lane);
+    float* sr = s_red + (grp_idx & 1) * (MG_CONS_WARPS * 32);  // double buffered: one barrier per group
+    ++grp_idx;
+    sr[warp * 32 + lane] = tot;
+    trace_ev(A, ctid, s_tr, 5);
+    cons_sync();
+    trace_ev(A, ctid, s_tr, 6);
+    // the last two consumer warps finish the outputs (with d_model >= 1280 they hold no K-slice, so this overlaps the
+    // other warps' next group; s_red is double buffered and the next cons_sync orders the reuse)
+    if (ctid >= MG_CONS - 64) {
+      const int et = ctid - (MG_CONS - 64);
+      const int p = et >> 5, i = et & 31;
+      const int j = i / NR, r = i - j * NR;
+      const int cj = p + n_parts * j;
+      if (p < n_parts && j < MG_GP && cj < nc && r < R) {
+        float v = 0.f;
+        for (int w = 0; w < wpp; ++w) v += sr[(p * wpp + w) * 32 + i];
+        const int n = g0 + cj;
+        if (g.bias != nullptr) v += bias_smem ? s_bias[n - lo] : __ldg(g.bias + n);
+        switch (g.epi) {
+          case GV_STORE:
+            g.out[static_cast<long long>(r) * g.ldo + n] = v;
+            break;
+          case GV_RESID: {  // residual columns are owned by this CTA for the whole pass: no global read-modify-write
+            const float nv = s_xown[r * 16 + (n - lo)] + v;
+            s_xown[r * 16 + (n - lo)] = nv;
+            g.out[static_cast<long long>(r) * g.ldo + n] = nv;
+            break;
+          }
+          case GV_GELU:
+            g.out[static_cast<long long>(r) * g.ldo + n] = gelu_erf(v);
+            break;
+          case GV_QKV: {
+            const int d = A.d;
+            if (n < d) {
+              g.out[static_cast<long long>(r) * g.ldo + n] = v;
+            } else {
+              const int pos = A.st->pos;
+              __half* cache = (n < 2 * d) ? ly->kcache : ly->vcache;
+              const int e = (n < 2 * d) ? n - d : n - 2 * d;
+              cache[(static_cast<long long>(r) * A.t_max + pos) * d + e] = __float2half_rn(v);
+            }
+            break;
+          }
+          default:
+            break;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ consumer: self-attention phase
+// task = (row, head); one warp does the work (sequence lengths are <= 448 and typically < 30)
+__device__ __noinline__ void consume_self_attn(const MegaArgs& A, const MegaLayer& ly, int ctid, float* s_p, unsigned short* s_slot) {
+  const int lane = ctid & 31, warp = ctid >> 5;
+  const int d = A.d, H = A.H;
+  const int pos = A.st->pos;
+  const int n_tasks = A.R * H;
+  for (int base = blockIdx.x * MG_CONS_WARPS; base < n_tasks; base += gridDim.x * MG_CONS_WARPS) {
+    const int task = base + warp;
+    if (task < n_tasks) {
+      const int r = task / H, h = task - r * H;
+      const int* indir = (*A.flip ? A.indir1 : A.indir0) + static_cast<long long>(r) * A.t_max;
+      const float* qr = A.q + static_cast<long long>(r) * d + h * HEAD_DIM;
+      float* sp = s_p + warp * 448;
+      unsigned short* ss = s_slot + warp * 448;
+      float qv[HEAD_DIM];
+#pragma unroll
+      for (int i = 0; i < HEAD_DIM / 4; ++i) {
+        const float4 v = ldcg_f4(qr + 4 * i);
+        qv[4 * i] = v.x; qv[4 * i + 1] = v.y; qv[4 * i + 2] = v.z; qv[4 * i + 3] = v.w;
+      }
+      float mx = -INFINITY;
+      for (int t = lane; t <= pos; t += 32) {
+        const int slot = (t == pos) ? r : indir[t];
+        ss[t] = static_cast<unsigned short>(slot);
+        const uint4* kr = reinterpret_cast<const uint4*>(ly.kcache + (static_cast<long long>(slot) * A.t_max + t) * d + h * HEAD_DIM);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 u = __ldcg(kr + i);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h2[j]);
+            s = fmaf(qv[8 * i + 2 * j], f.x, s);
+            s = fmaf(qv[8 * i + 2 * j + 1], f.y, s);
+          }
+        }
+        s *= 0.125f;
+        sp[t] = s;
+        mx = fmaxf(mx, s);
+      }
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int t = lane; t <= pos; t += 32) {
+        const float p = __expf(sp[t] - mx);
+        sp[t] = p;
+        sum += p;
+      }
+      sum = warp_sum(sum);
+      __syncwarp();
+      float o0 = 0.f, o1 = 0.f;
+      for (int t = 0; t <= pos; ++t) {
+        const float p = sp[t];
+        const unsigned vv = __ldcg(reinterpret_cast<const unsigned*>(ly.vcache + (static_cast<long long>(ss[t]) * A.t_max + t) * d +
+                                                                   h * HEAD_DIM + 2 * lane));
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&vv));
+        o0 = fmaf(p, f.x, o0);
+        o1 = fmaf(p, f.y, o1);
+      }
+      const float inv = 1.0f / sum;
+      *reinterpret_cast<float2*>(A.ctx + static_cast<long long>(r) * d + h * HEAD_DIM + 2 * lane) = make_float2(o0 * inv, o1 * inv);
+      __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------ consumer: cross-attention phase
+// task = (utterance, head, key split); K and V chunks arrive through the ring; 40 groups of 8 lanes walk the keys with
+// an online softmax for all beams at once, merged through shared memory into one partial (acc[64], m, l) per beam.
+template <int NB>
+__device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid, float* s_part, int* s_flag) {
+  const CrossGeom cg = cross_geom(A.n_utt, A.H);
+  const int grp = ctid >> 3, gl = ctid & 7;
+  constexpr int NGRP = MG_CONS / 8;  // 40
+  const int d = A.d, beam = A.beam;
+  const unsigned gmask = 0xFFu << (ctid & 24);
+  for (int task = blockIdx.x; task < cg.n_tasks; task += gridDim.x) {
+    const int split = task % cg.S, uh = task / cg.S;
+    const int u = uh / A.H, h = uh - u * A.H;
+    const int t0 = split * cg.KS;
+    const int nk = min(cg.KS, T_ENC_PAD - t0);
+    float qv[NB][8];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) qv[k][i] = 0.f;
+      if (k < beam) {
+        const float* qr = A.q + static_cast<long long>(u * beam + k) * d + h * HEAD_DIM + gl * 8;
+        const float4 a0 = ldcg_f4(qr), a1 = ldcg_f4(qr + 4);
+        qv[k][0] = a0.x; qv[k][1] = a0.y; qv[k][2] = a0.z; qv[k][3] = a0.w;
+        qv[k][4] = a1.x; qv[k][5] = a1.y; qv[k][6] = a1.z; qv[k][7] = a1.w;
+      }
+    }
+    const int stK = rg.unit % MG_NSTAGE;
+    const unsigned phK = (rg.unit / MG_NSTAGE) & 1u;
+    const int stV = (rg.unit + 1) % MG_NSTAGE;
+    const unsigned phV = ((rg.unit + 1) / MG_NSTAGE) & 1u;
+    mbar_wait(rg.full(stK), phK);
+    mbar_wait(rg.full(stV), phV);
+    const __half* sK = reinterpret_cast<const __half*>(rg.data + stK * MG_STAGE_BYTES);
+    const __half* sV = reinterpret_cast<const __half*>(rg.data + stV * MG_STAGE_BYTES);
+    float m[NB], l[NB], acc[NB][8];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      m[k] = -INFINITY;
+      l[k] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
+    }
+#pragma unroll 1
+    for (int tl = grp; tl < nk; tl += NGRP) {
+      if (t0 + tl >= T_ENC) break;
+      const uint4 ku = *reinterpret_cast<const uint4*>(sK + tl * HEAD_DIM + gl * 8);
+      const uint4 vu = *reinterpret_cast<const uint4*>(sV + tl * HEAD_DIM + gl * 8);
+      float kf[8], vf[8];
+      {
+        const __half2* k2 = reinterpret_cast<const __half2*>(&ku);
+        const __half2* v2 = reinterpret_cast<const __half2*>(&vu);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 a = __half22float2(k2[i]), b = __half22float2(v2[i]);
+          kf[2 * i] = a.x; kf[2 * i + 1] = a.y;
+          vf[2 * i] = b.x; vf[2 * i + 1] = b.y;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(qv[k][i], kf[i], s);
+        s += __shfl_xor_sync(gmask, s, 1);
+        s += __shfl_xor_sync(gmask, s, 2);
+        s += __shfl_xor_sync(gmask, s, 4);
+        s *= 0.125f;
+        const float mn = fmaxf(m[k], s);
+        const float al = __expf(m[k] - mn), p = __expf(s - mn);
+        l[k] = l[k] * al + p;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[k][i] = fmaf(acc[k][i], al, p * vf[i]);
+        m[k] = mn;
+      }
+    }
+    __syncwarp();
+    if ((ctid & 31) == 0) {
+      mbar_arrive(rg.empty(stK));
+      mbar_arrive(rg.empty(stV));
+    }
+    rg.unit += 2;
+    // merge: first the 4 groups of a warp with shuffles (lanes l, l^8, l^16 hold the same dims), then the 10 warps
+    // through shared memory: s_part[warp][k][66]
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+#pragma unroll
+      for (int off = 8; off <= 16; off <<= 1) {
+        const float mo = __shfl_xor_sync(0xffffffffu, m[k], off);
+        const float lo_ = __shfl_xor_sync(0xffffffffu, l[k], off);
+        const float mn = fmaxf(m[k], mo);
+        const float wa = (m[k] == -INFINITY) ? 0.f : __expf(m[k] - mn);
+        const float wb = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
+        l[k] = l[k] * wa + lo_ * wb;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float ao = __shfl_xor_sync(0xffffffffu, acc[k][i], off);
+          acc[k][i] = acc[k][i] * wa + ao * wb;
+        }
+        m[k] = mn;
+      }
+      if ((ctid & 31) < 8) {
+        float* dst = s_part + ((ctid >> 5) * NB + k) * 66;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[gl * 8 + i] = acc[k][i];
+        if (gl == 0) {
+          dst[64] = m[k];
+          dst[65] = l[k];
+        }
+      }
+    }
+    cons_sync();
+    for (int idx = ctid; idx < beam * HEAD_DIM; idx += MG_CONS) {
+      const int k = idx / HEAD_DIM, e = idx - k * HEAD_DIM;
+      float mm = -INFINITY;
+      for (int g = 0; g < MG_CONS_WARPS; ++g) mm = fmaxf(mm, s_part[(g * NB + k) * 66 + 64]);
+      float a = 0.f, ll = 0.f;
+      for (int g = 0; g < MG_CONS_WARPS; ++g) {
+        const float mg = s_part[(g * NB + k) * 66 + 64];
+        const float w = (mg == -INFINITY) ? 0.f : __expf(mg - mm);
+        a = fmaf(w, s_part[(g * NB + k) * 66 + e], a);
+        ll = fmaf(w, s_part[(g * NB + k) * 66 + 65], ll);
+      }
+      float* out = A.cross_part + (static_cast<long long>(uh) * cg.S + split) * (MAX_BEAM * 68) + k * 68;
+      out[e] = a;
+      if (e == 0) {
+        out[64] = mm;
+        out[65] = ll;
+      }
+    }
+    // split-K style fix-up: the last split of (utterance, head) to arrive merges all partials into ctx
+    __threadfence();
+    cons_sync();
+    if (ctid == 0) {
+      const unsigned prev = atomicAdd(A.cross_count + uh, 1u);
+      s_flag[0] = (prev == static_cast<unsigned>(cg.S - 1)) ? 1 : 0;
+      if (s_flag[0]) A.cross_count[uh] = 0;  // reset for the next layer (ordered by the grid barriers)
+    }
+    cons_sync();
+    if (s_flag[0]) {
+      __threadfence();
+      for (int idx = ctid; idx < beam * HEAD_DIM; idx += MG_CONS) {
+        const int k = idx / HEAD_DIM, e = idx - k * HEAD_DIM;
+        const float* pb = A.cross_part + (static_cast<long long>(uh) * cg.S) * (MAX_BEAM * 68) + k * 68;
+        float mm = -INFINITY;
+        for (int s2 = 0; s2 < cg.S; ++s2) mm = fmaxf(mm, ldcg_f(pb + s2 * (MAX_BEAM * 68) + 64));
+        float a = 0.f, ll = 0.f;
+        for (int s2 = 0; s2 < cg.S; ++s2) {
+          const float ms = ldcg_f(pb + s2 * (MAX_BEAM * 68) + 64);
+          const float w = (ms == -INFINITY) ? 0.f : __expf(ms - mm);
+          a = fmaf(w, ldcg_f(pb + s2 * (MAX_BEAM * 68) + e), a);
+          ll = fmaf(w, ldcg_f(pb + s2 * (MAX_BEAM * 68) + 65), ll);
+        }
+        A.ctx[static_cast<long long>(u * beam + k) * d + h * HEAD_DIM + e] = a / ll;
+      }
+    }
+    cons_sync();
+  }
+}
+
+template <int NR>
+__global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs A) {
+  extern __shared__ __align__(1024) uint8_t mg_smem[];
+  uint8_t* ring_data = mg_smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mg_smem + MG_NSTAGE * MG_STAGE_BYTES);
+  float* s_red = reinterpret_cast<float*>(mg_smem + MG_NSTAGE * MG_STAGE_BYTES + 1024);
+  float* s_stat = s_red + 2 * MG_CONS_WARPS * 32;
+  float* s_part = s_stat + 1024;  // [40][NB][66] for the cross-attention merge; also self-attention scratch
+  Ring rg;
+  rg.data = ring_data;
+  rg.data0 = smem_u32(ring_data);
+  rg.full0 = smem_u32(bars);
+  rg.empty0 = rg.full0 + 8 * MG_NSTAGE;
+  rg.unit = 0;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < MG_NSTAGE; ++s) {
+      mbar_init(rg.full(s), 1);
+      mbar_init(rg.empty(s), MG_CONS_WARPS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int L = A.n_layers;
+
+  if (tid >= MG_CONS) {
+    // ============================ producer: the static weight / KV stream of this CTA
+    if (tid == MG_CONS) {
+      for (int l = 0; l < L; ++l) {
+        const MegaLayer& ly = A.layers[l];
+        produce_gemv(rg, ly.qkv, mg_gp(NR));
+        produce_gemv(rg, ly.o, mg_gp(NR));
+        produce_gemv(rg, ly.cq, mg_gp(NR));
+        produce_cross(rg, A, ly);
+        produce_gemv(rg, ly.co, mg_gp(NR));
+        produce_gemv(rg, ly.fc1, mg_gp(NR));
+        produce_gemv(rg, ly.fc2, mg_gp(NR));
+      }
+      if (A.with_logits) produce_gemv(rg, A.vocab, mg_gp(NR));
+    }
+    return;
+  }
+  // ============================== consumers
+  const int ctid = tid;
+  unsigned epoch = *A.epoch_base;  // flags hold the epoch of the previous launch
+  const unsigned epoch0 = epoch;
+  if (ctid == 0) *reinterpret_cast<int*>(s_stat + 1001) = 0;
+  if (A.trace != nullptr && blockIdx.x == 0 && ctid == 0) A.trace[0] = globaltimer_ns();
+  // phase 0: token + positional embedding; every CTA produces (and keeps) the residual-stream columns it owns
+  {
+    const int pos = A.st->pos;
+    int lo, hi;
+    cta_cols(A.d, lo, hi);
+    float* s_xown = s_stat + 768;
+    for (int idx = ctid; idx < A.R * (hi - lo); idx += MG_CONS) {
+      const int r = idx / (hi - lo), c = idx - r * (hi - lo);
+      const float v = __half2float(A.tok_emb[static_cast<long long>(A.tokens[r]) * A.d + lo + c]) +
+                      A.pos_emb[static_cast<long long>(pos) * A.d + lo + c];
+      s_xown[r * 16 + c] = v;
+      A.x[static_cast<long long>(r) * A.d + lo + c] = v;
+    }
+  }
+  grid_barrier(A, epoch, ctid, epoch0);
+  for (int l = 0; l < L; ++l) {
+    const MegaLayer& ly = A.layers[l];
+    consume_gemv<NR>(rg, A, ly.qkv, &ly, ctid, s_red, s_stat, s_part);
+    grid_barrier(A, epoch, ctid, epoch0);
+    consume_self_attn(A, ly, ctid, s_part, reinterpret_cast<unsigned short*>(s_part + MG_CONS_WARPS * 448));
+    grid_barrier(A, epoch, ctid, epoch0);
+    consume_gemv<NR>(rg, A, ly.o, &ly, ctid, s_red, s_stat, s_part);
+    grid_barrier(A, epoch, ctid, epoch0);
+    consume_gemv<NR>(rg, A, ly.cq, &ly, ctid, s_red, s_stat, s_part);
+    grid_barrier(A, epoch, ctid, epoch0);
+    consume_cross<NR>(rg, A, ctid, s_part, reinterpret_cast<int*>(s_stat + 1000));  // beam <= rows <= NR
+    grid_barrier(A, epoch, ctid, epoch0);
+    consume_gemv<NR>(rg, A, ly.co, &ly, ctid, s_red, s_stat, s_part);
+    grid_barrier(A, epoch, ctid, epoch0);
+    consume_gemv<NR>(rg, A, ly.fc1, &ly, ctid, s_red, s_stat, s_part);
+    grid_barrier(A, epoch, ctid, epoch0);
+    consume_gemv<NR>(rg, A, ly.fc2, &ly, ctid, s_red, s_stat, s_part);
+    grid_barrier(A, epoch, ctid, epoch0);
+  }
+  if (A.with_logits) consume_gemv<NR>(rg, A, A.vocab, nullptr, ctid, s_red, s_stat, s_part);
+  // publish the final epoch for the next launch (every CTA leaves the same value behind)
+  grid_barrier(A, epoch, ctid, epoch0);
+  if (blockIdx.x == 0 && ctid == 0) *A.epoch_base = epoch;
+}
+
+__global__ void chunk_major_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int N, int K, int n_chunks) {
+  const int kc = K / n_chunks;
+  const long long total = static_cast<long long>(N) * K / 8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long e = i * 8;
+    const int n = static_cast<int>(e / K), k = static_cast<int>(e - static_cast<long long>(n) * K);
+    const int c = k / kc, kk = k - c * kc;
+    *reinterpret_cast<uint4*>(dst + (static_cast<long long>(c) * N + n) * kc + kk) = *reinterpret_cast<const uint4*>(src + e);
+  }
+}
+
+}  // namespace
+
+int mega_k_chunks(int K) {
+  int n = (K + MG_KC_MAX - 1) / MG_KC_MAX;
+  while (K % (8 * n) != 0) ++n;
+  return n;
+}
+
+// W [N][K] -> [chunk][N][K / n_chunks]: every (chunk, row range) the pass kernel streams becomes one contiguous block
+void mega_chunk_major(const __half* src, __half* dst, int N, int K, cudaStream_t stream) {
+  chunk_major_kernel<<<1024, 256, 0, stream>>>(src, dst, N, K, mega_k_chunks(K));
+  WISB_CUDA(cudaGetLastError());
+}
+
+size_t mega_flags_words() { return 160 * 32 + 32; }
+
+void dec_pass_run(const MegaArgs& a, int num_sms, cudaStream_t stream) {
+  WISB_REQUIRE(a.R >= 1 && a.R <= 8, "decoder pass: 1..8 rows");
+  WISB_REQUIRE(a.d % 64 == 0 && a.d <= MG_KC_MAX, "decoder pass: d_model <= 1536");
+  WISB_REQUIRE((a.d + num_sms - 1) / num_sms <= 16, "decoder pass: too few SMs for the per-CTA residual slice");
+  WISB_REQUIRE(num_sms <= 160, "decoder pass: more SMs than barrier flags");
+  static bool attr_set = false;
+  if (!attr_set) {
+    WISB_CUDA(cudaFuncSetAttribute(dec_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
+    WISB_CUDA(cudaFuncSetAttribute(dec_pass_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
+    WISB_CUDA(cudaFuncSetAttribute(dec_pass_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
+    attr_set = true;
+  }
+  void* args[] = {const_cast<MegaArgs*>(&a)};
+  const void* fn = a.R <= 2 ? reinterpret_cast<const void*>(dec_pass_kernel<2>)
+                            : a.R <= 5 ? reinterpret_cast<const void*>(dec_pass_kernel<5>)
+                                       : reinterpret_cast<const void*>(dec_pass_kernel<8>);
+  WISB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(num_sms), dim3(MG_THREADS), args, MG_SMEM, stream));
+}
+
+}  // namespace wisb

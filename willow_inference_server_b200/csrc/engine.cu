@@ -107,7 +107,7 @@ struct wisb_handle {
   std::map<std::string, TensorRef> tensors;
   std::vector<DecLayerW> dec_w;
   // options
-  int use_graphs = 1, attn_v_mn = 1, attn_ref = 0, decode_poll = 1;
+  int use_graphs = 1, attn_v_mn = 1, attn_ref = 0, decode_poll = 1, decoder_mega = 1;
   // front end
   DevBuf<float> lm_tables;
   DevBuf<unsigned> lm_max;
@@ -133,6 +133,14 @@ struct wisb_handle {
   DevBuf<unsigned long long> part;
   DevBuf<int> cand_idx, tokens, seq0, seq1, ind0, ind1, flip, done, n_hyp, best_len, best_tokens, prompt_dev, lang_ids;
   DevBuf<DecState> st;
+  DevBuf<MegaLayer> mega_layers;
+  DevBuf<unsigned> mega_flags;
+  DevBuf<float> cross_part;
+  DevBuf<unsigned> cross_count;
+  DevBuf<__half> fc2_chunked;  // decoder fc2 weights in chunk-major layout for the persistent pass kernel
+  DevBuf<unsigned long long> mega_trace;
+  int mega_trace_on = 0;
+  PinBuf<MegaLayer> mega_layers_host;
   PinBuf<int> pin_i;
   PinBuf<float> pin_f;
   PinBuf<uint8_t> pin_b;
@@ -295,6 +303,17 @@ void finish_create(wisb_handle* h) {
   h->best_tokens.ensure(R * T_MAX, true);
   h->prompt_dev.ensure(R * T_MAX);
   h->st.ensure(1, true);
+  h->mega_layers.ensure(d.n_dec_layers);
+  h->mega_layers_host.ensure(d.n_dec_layers);
+  h->mega_flags.ensure(mega_flags_words(), true);
+  h->cross_count.ensure(static_cast<size_t>(DEC_MAX_ROWS) * d.n_heads, true);
+  if (mega_k_chunks(4 * d.d_model) > 1) {
+    const size_t per = static_cast<size_t>(4) * d.d_model * d.d_model;
+    h->fc2_chunked.ensure(per * d.n_dec_layers);
+    for (int i = 0; i < d.n_dec_layers; ++i)
+      mega_chunk_major(h->dec_w[i].fc2w, h->fc2_chunked.p + per * i, d.d_model, 4 * d.d_model, h->stream);
+  }
+  h->cross_part.ensure(static_cast<size_t>(DEC_MAX_ROWS) * d.n_heads * 16 * MAX_BEAM * 68, true);
   h->lang_probs.ensure(R * 128);
   h->pin_i.ensure(4 + R * (T_MAX + 2));
   h->pin_f.ensure(R * 130);
@@ -494,8 +513,82 @@ SearchArgs make_search_args(wisb_handle* h, const DecodeCfg& c) {
   return a;
 }
 
+// descriptors of the persistent decoder pass for this batch slice (device array of per-layer pointers)
+void upload_mega_layers(wisb_handle* h, const DecodeCfg& c) {
+  const Dims& dm = h->dims;
+  const int d = dm.d_model, H = dm.n_heads;
+  const size_t layer_cache = static_cast<size_t>(DEC_MAX_ROWS) * T_MAX * d;
+  const size_t head_block = static_cast<size_t>(H) * T_ENC_PAD * HEAD_DIM;
+  for (int i = 0; i < dm.n_dec_layers; ++i) {
+    const DecLayerW& w = h->dec_w[i];
+    MegaLayer& m = h->mega_layers_host.p[i];
+    m = MegaLayer();
+    auto set = [&](MegaGemv& g, const __half* wt, const float* bias, const float* lg, const float* lb, const float* x,
+                   float* out, long long ldo, int N, int K, int epi) {
+      g.w = wt; g.bias = bias; g.ln_g = lg; g.ln_b = lb; g.x = x; g.out = out; g.ldo = ldo; g.N = N; g.K = K; g.epi = epi;
+    };
+    set(m.qkv, w.qkvw, w.qkvb, w.ln1g, w.ln1b, h->dx.p, h->dq.p, d, 3 * d, d, GV_QKV);
+    set(m.o, w.ow, w.ob, nullptr, nullptr, h->dctx.p, h->dx.p, d, d, d, GV_RESID);
+    set(m.cq, w.cqw, w.cqb, w.ln2g, w.ln2b, h->dx.p, h->dq.p, d, d, d, GV_STORE);
+    set(m.co, w.cow, w.cob, nullptr, nullptr, h->dctx.p, h->dx.p, d, d, d, GV_RESID);
+    set(m.fc1, w.fc1w, w.fc1b, w.ln3g, w.ln3b, h->dx.p, h->dh.p, 4 * d, 4 * d, d, GV_GELU);
+    const __half* fc2w = h->fc2_chunked.p ? h->fc2_chunked.p + static_cast<size_t>(4) * d * d * i : w.fc2w;
+    set(m.fc2, fc2w, w.fc2b, nullptr, nullptr, h->dh.p, h->dx.p, d, d, 4 * d, GV_RESID);
+    m.ck = h->ckv.p + (static_cast<size_t>(i * 2 + 0) * c.B_total + c.u0) * head_block;
+    m.cv = h->ckv.p + (static_cast<size_t>(i * 2 + 1) * c.B_total + c.u0) * head_block;
+    m.kcache = h->kcache.p + i * layer_cache;
+    m.vcache = h->vcache.p + i * layer_cache;
+  }
+  WISB_CUDA(cudaMemcpyAsync(h->mega_layers.p, h->mega_layers_host.p, sizeof(MegaLayer) * dm.n_dec_layers,
+                            cudaMemcpyHostToDevice, h->stream));
+}
+
+int enqueue_decoder_forward_mega(wisb_handle* h, const DecodeCfg& c, bool with_logits) {
+  const Dims& dm = h->dims;
+  MegaArgs a;
+  a.layers = h->mega_layers.p;
+  a.n_layers = dm.n_dec_layers;
+  a.vocab.w = h->H("dec.tok_emb");
+  a.vocab.ln_g = h->F("dec.ln.g");
+  a.vocab.ln_b = h->F("dec.ln.b");
+  a.vocab.x = h->dx.p;
+  a.vocab.out = h->logits.p;
+  a.vocab.ldo = dm.n_vocab_pad;
+  a.vocab.N = dm.n_vocab;
+  a.vocab.K = dm.d_model;
+  a.vocab.epi = GV_STORE;
+  a.with_logits = with_logits ? 1 : 0;
+  a.R = c.n_utt * c.beam;
+  a.d = dm.d_model;
+  a.H = dm.n_heads;
+  a.n_utt = c.n_utt;
+  a.beam = c.beam;
+  a.t_max = T_MAX;
+  a.tokens = h->tokens.p;
+  a.tok_emb = h->H("dec.tok_emb");
+  a.pos_emb = h->F("dec.pos");
+  a.x = h->dx.p;
+  a.q = h->dq.p;
+  a.ctx = h->dctx.p;
+  a.indir0 = h->ind0.p;
+  a.indir1 = h->ind1.p;
+  a.flip = h->flip.p;
+  a.st = h->st.p;
+  a.cross_part = h->cross_part.p;
+  a.cross_count = h->cross_count.p;
+  a.flags = h->mega_flags.p;
+  a.epoch_base = h->mega_flags.p + 160 * 32;
+  if (h->mega_trace_on) {
+    h->mega_trace.ensure(2048, true);
+    a.trace = h->mega_trace.p;
+  }
+  dec_pass_run(a, h->num_sms, h->stream);
+  return 1;
+}
+
 // one decoder forward for R rows at position st->pos; returns kernels launched
 int enqueue_decoder_forward(wisb_handle* h, const DecodeCfg& c, bool with_logits) {
+  if (h->decoder_mega) return enqueue_decoder_forward_mega(h, c, with_logits);
   const Dims& dm = h->dims;
   const int d = dm.d_model, H = dm.n_heads, R = c.n_utt * c.beam;
   cudaStream_t s = h->stream;
@@ -623,14 +716,17 @@ int decode_pass(wisb_handle* h, const DecodeCfg& c, const int32_t* prompts, int3
   WISB_CUDA(cudaMemcpyAsync(h->prompt_dev.p, h->pin_i.p + 4, sizeof(int) * c.n_utt * c.prompt_len, cudaMemcpyHostToDevice, s));
   SearchArgs sa = make_search_args(h, c);
   search_init_run(sa, h->prompt_dev.p, s);
+  if (h->decoder_mega) upload_mega_layers(h, c);
   if (c.max_new > 0) {
-    DecGraphs* g = h->use_graphs ? &get_graphs(h, c) : nullptr;
+    // the persistent pass kernel is a handful of launches per step: no graph needed (and it is a cooperative launch)
+    DecGraphs* g = (h->use_graphs && !h->decoder_mega) ? &get_graphs(h, c) : nullptr;
     for (int p = 0; p + 1 < c.prompt_len; ++p) {
       if (g) WISB_CUDA(cudaGraphLaunch(g->prefill, s)); else enqueue_prefill(h, c);
       ++steps;
     }
-    const int per_step = 1 + 8 * h->dims.n_dec_layers + 1 + 4;
-    h->launches += (c.prompt_len - 1) * (per_step - 4);
+    const int fwd = h->decoder_mega ? 1 : 1 + 8 * h->dims.n_dec_layers + 1;
+    const int per_step = fwd + 4;
+    h->launches += (c.prompt_len - 1) * (fwd + 1);
     volatile int* flag = h->pin_i.p;
     *flag = 0;
     for (int gs = 0; gs < c.max_new; ++gs) {
@@ -818,6 +914,8 @@ int wisb_set_option(wisb_handle* h, const char* key, int value) {
     else if (k == "attn_ref") h->attn_ref = value;
     else if (k == "decode_poll") h->decode_poll = value < 1 ? 1 : value;
     else if (k == "profile") h->profile = value;
+    else if (k == "decoder_mega") h->decoder_mega = value;
+    else if (k == "mega_trace") h->mega_trace_on = value;
     else throw Error(1, "unknown option '" + k + "'");
   });
 }
@@ -949,6 +1047,7 @@ int wisb_detect_language(wisb_handle* h, const float* mel, int B, int32_t* lang_
       memcpy(h->pin_i.p + 4, sot.data(), sizeof(int) * c.n_utt);
       WISB_CUDA(cudaMemcpyAsync(h->prompt_dev.p, h->pin_i.p + 4, sizeof(int) * c.n_utt, cudaMemcpyHostToDevice, s));
       search_init_run(make_search_args(h, c), h->prompt_dev.p, s);
+      if (h->decoder_mega) upload_mega_layers(h, c);
       enqueue_decoder_forward(h, c, true);
       lang_probs_run(h->logits.p, dm.n_vocab_pad, h->lang_ids.p, nl, c.n_utt, 1, h->lang_probs.p, s);
       WISB_CUDA(cudaMemcpyAsync(h->pin_f.p, h->lang_probs.p, sizeof(float) * c.n_utt * nl, cudaMemcpyDeviceToHost, s));
@@ -995,6 +1094,14 @@ int wisb_debug_gemm(wisb_handle* h, const uint16_t* a, const uint16_t* w, float*
   });
 }
 
+int wisb_debug_read_trace(wisb_handle* h, unsigned long long* out, int n) {
+  return guarded(h, [&] {
+    WISB_REQUIRE(out != nullptr && n > 0 && n <= 2048, "bad arguments");
+    h->mega_trace.ensure(2048, true);
+    WISB_CUDA(cudaMemcpy(out, h->mega_trace.p, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
+  });
+}
+
 int wisb_debug_encode(wisb_handle* h, const float* mel, int B, float* enc_out, int n_layers) {
   return guarded(h, [&] {
     WISB_REQUIRE(h->blob != nullptr && enc_out != nullptr && B >= 1, "bad arguments");
@@ -1024,6 +1131,7 @@ int wisb_debug_forced_logits(wisb_handle* h, const float* mel, const int32_t* to
     memcpy(h->pin_i.p + 4, tokens, sizeof(int) * n_tokens);
     WISB_CUDA(cudaMemcpyAsync(h->prompt_dev.p, h->pin_i.p + 4, sizeof(int) * n_tokens, cudaMemcpyHostToDevice, s));
     search_init_run(make_search_args(h, c), h->prompt_dev.p, s);
+    if (h->decoder_mega) upload_mega_layers(h, c);
     for (int p = 0; p < n_tokens; ++p) {
       enqueue_decoder_forward(h, c, true);
       WISB_CUDA(cudaMemcpyAsync(logits_out + static_cast<size_t>(p) * dm.n_vocab, h->logits.p, sizeof(float) * dm.n_vocab, cudaMemcpyDeviceToHost, s));
