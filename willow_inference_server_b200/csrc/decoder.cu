@@ -219,9 +219,9 @@ gemv_kernel(const GemvArgs a) {
             }
           }
 #pragma unroll
-          for (int c = 0; c < C; ++c)
+          for (int i = 0; i < 8; ++i)  // k-element outermost: C independent chains per row are interleaved
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[c][r] = fmaf(xv[i], wf[c][i], acc[c][r]);
+            for (int c = 0; c < C; ++c) acc[c][r] = fmaf(xv[i], wf[c][i], acc[c][r]);
         }
       }
     }

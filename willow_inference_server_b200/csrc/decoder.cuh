@@ -95,8 +95,8 @@ void search_init_run(const SearchArgs& a, const int* prompt, cudaStream_t stream
 struct MegaGemv {
   const __half* w = nullptr;     // [N, K] fp16; K > 1536: chunk-major [chunk][N][K/chunks] (mega_chunk_major)
   const float* bias = nullptr;
-  const float* ln_g = nullptr;   // LayerNorm on x when non-null (K <= 1536)
-  const float* ln_b = nullptr;
+  const float* ln_g = nullptr;   // LayerNorm gamma (x is multiplied by it while staged), K <= 1536
+  const float* ln_s2 = nullptr;  // non-null = LayerNorm folded: s2[n] = sum_k g_k W[n,k]; `bias` then holds bias + sum_k b_k W[n,k]
   const float* x = nullptr;      // [R, K] fp32 activations
   float* out = nullptr;
   long long ldo = 0;
@@ -134,6 +134,9 @@ struct MegaArgs {
 size_t mega_flags_words();
 int mega_k_chunks(int K);
 void mega_chunk_major(const __half* src, __half* dst, int N, int K, cudaStream_t stream);
+// s2[n] = sum_k g[k] W[n,k];  biasf[n] = bias[n] + sum_k b[k] W[n,k]   (bias may be null)
+void mega_ln_fold(const __half* w, const float* g, const float* b, const float* bias, float* s2, float* biasf, int N, int K,
+                  cudaStream_t stream);
 void dec_pass_run(const MegaArgs& a, int num_sms, cudaStream_t stream);
 
 // language detection head: softmax over lang ids of the logits of row u*beam (one step on <|startoftranscript|>)

@@ -35,13 +35,21 @@ constexpr int MG_STAGE_BYTES = 12 * MG_KC_MAX * 2;      // 36864: up to 12 weigh
 constexpr int MG_NSTAGE = 5;
 constexpr int MG_CA_KEYS_MAX = MG_STAGE_BYTES / 128;    // 288 keys per K (or V) chunk
 constexpr int MG_SCRATCH = 28672;                       // self-attention probabilities / cross-attention merge
-constexpr int MG_SMEM = MG_NSTAGE * MG_STAGE_BYTES + 1024 + 2 * MG_CONS_WARPS * 32 * 4 + 4096 + MG_SCRATCH;
+constexpr int MG_RED_FLOATS = (2 * 2 + 1) * MG_CONS_WARPS * 32;  // 2 buffers x 2 sets + LN partials
+constexpr int MG_SMEM = MG_NSTAGE * MG_STAGE_BYTES + 1024 + MG_RED_FLOATS * 4 + 4224 + MG_SCRATCH;
 // columns a thread accumulates per unit: the transposing reduction handles GP * NR <= 32 values
 __host__ __device__ constexpr int mg_gp(int nr) { return 32 / nr < 6 ? 32 / nr : 6; }
+// accumulator sets per thread: 2 x 6 columns for <= 5 rows (the stage holds 12 weight-row chunks), 1 x 4 for 8 rows
+__host__ __device__ constexpr int mg_nset(int nr) { return nr <= 5 ? 2 : 1; }
 
 __device__ __forceinline__ float ldcg_f(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ float4 ldcg_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(MG_CONS) : "memory"); }
 
 // in: lane l holds v[0..31]; out: v[0] of lane l = sum over all lanes of their v[l]
@@ -110,6 +118,9 @@ __device__ __noinline__ void produce_gemv(Ring& rg, const MegaGemv& g, int gp) {
   }
 }
 
+// cross-attention: task = (utterance, head, key split): the 1500 keys of a head are split over S CTAs (one K unit and
+// one V unit of <= 288 keys each through the ring); the last split to finish merges the partials (split-K fix-up).
+// (One CTA per head without a split was measured 3x slower: the online-softmax walk over 1500 keys is compute-bound.)
 struct CrossGeom {
   int S, KS, n_tasks;
 };
@@ -130,7 +141,7 @@ __device__ __noinline__ void produce_cross(Ring& rg, const MegaArgs& A, const Me
   for (int task = blockIdx.x; task < cg.n_tasks; task += gridDim.x) {
     const int split = task % cg.S, uh = task / cg.S;
     const int t0 = split * cg.KS;
-    const int nk = min(cg.KS, T_ENC_PAD - t0);  // buffer has 1536 rows; keys >= 1500 are masked by the consumer
+    const int nk = min(cg.KS, T_ENC_PAD - t0);  // buffer has 1536 rows; keys >= 1500 are skipped by the consumer
     const long long off = (static_cast<long long>(uh) * T_ENC_PAD + t0) * HEAD_DIM;
     for (int kv = 0; kv < 2; ++kv) {
       const int st = rg.unit % MG_NSTAGE;
@@ -143,7 +154,6 @@ __device__ __noinline__ void produce_cross(Ring& rg, const MegaArgs& A, const Me
   }
 }
 
-// ------------------------------------------------------------------ grid barrier (consumers only)
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -187,35 +197,50 @@ __device__ __forceinline__ void grid_barrier(const MegaArgs& A, unsigned& epoch,
 }
 
 // ------------------------------------------------------------------ consumer: one GEMV phase
+// Thread (part, kv) keeps the K-slice kv of every row in registers and streams the unit's columns
+// cj = part + n_parts * m (m < NSET * GP) through it.  LayerNorm is folded (s2 / folded bias precomputed at load):
+//     LN(x) . w + bias = rstd * (sum_k x_k g_k w_k - mean * s2[n]) + biasf[n]
+// so the row statistics are only needed in the epilogue and their reduction rides along with the first group's.
 template <int NR>
-__device__ __noinline__ void consume_gemv(Ring& rg, const MegaArgs& A, const MegaGemv& g, const MegaLayer* ly, int ctid,
-                                          float* s_red, float* s_stat, float* s_comb) {
+__device__ __noinline__ void consume_gemv(Ring& rg, const MegaArgs& A, const MegaGemv& g_mem, const MegaLayer* ly, int ctid,
+                                          float* s_red, float* s_stat) {
+  const MegaGemv g = g_mem;  // descriptor into registers once (it lives in global memory)
+  const uint32_t ring_data0 = rg.data0, ring_full0 = rg.full0, ring_empty0 = rg.empty0;
+  unsigned unit = rg.unit;
+  constexpr int GP = mg_gp(NR);
+  constexpr int NSET = mg_nset(NR);
+  constexpr int NACC = GP * NSET;
   const int lane = ctid & 31, warp = ctid >> 5;
   const int R = A.R;
-  int lo, hi, n_chunks, kc;
+  int lo, hi, n_chunks, kc, wpp, n_parts;
   cta_cols(g.N, lo, hi);
   k_split(g.K, n_chunks, kc);
-  constexpr int MG_GP = mg_gp(NR);
-  const int n_kvec = kc / 8;
-  int wpp, n_parts;
   part_geom(kc, wpp, n_parts);
-  const int MG_G = MG_GP * n_parts;
+  const int G = NACC * n_parts;
+  const int n_kvec = kc / 8;
   const int part = warp / wpp;
   const int kv = (warp - part * wpp) * 32 + lane;
   const bool active = part < n_parts && kv < n_kvec;
-  const bool ln = g.ln_g != nullptr;
-
+  const bool ln = g.ln_s2 != nullptr;
   int* s_tr = reinterpret_cast<int*>(s_stat + 1001);
   trace_ev(A, ctid, s_tr, 1);
-  float* s_bias = s_stat + 256;   // [<=512] this CTA's bias slice, prefetched while x is in flight
-  float* s_xown = s_stat + 768;   // [8][16]  residual-stream columns owned by this CTA (kept across phases)
+  float* s_bias = s_stat + 256;        // [<=256] bias (LN: folded bias) of this CTA's columns
+  float* s_s2 = s_stat + 512;          // [<=256] LN fold vector of this CTA's columns
+  float* s_xown = s_stat + 768;        // [8][16] residual-stream columns owned by this CTA (kept across phases)
+  float* s_lnred = s_red + 2 * NSET * MG_CONS_WARPS * 32;  // [warps][32] per-warp partial row sums (LN)
   const int ncols = hi - lo;
-  const bool bias_smem = g.bias != nullptr && ncols <= 512;
-  if (bias_smem)
-    for (int i = ctid; i < ncols; i += MG_CONS) s_bias[i] = __ldg(g.bias + lo + i);
-  float acc[MG_GP][NR];
+  const bool pre = ncols <= 256;
+  if (pre) {
+    for (int i = ctid; i < ncols; i += MG_CONS) {
+      s_bias[i] = g.bias != nullptr ? __ldg(g.bias + lo + i) : 0.f;
+      if (ln) s_s2[i] = __ldg(g.ln_s2 + lo + i);
+    }
+  }
+  float acc[NACC][NR];
   float xv[NR][8], xn[NR][8];
-  int grp_idx = 0;
+  float sx[NR], sxx[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) sx[r] = sxx[r] = 0.f;
   auto load_x = [&](float (&dst)[NR][8], int ch) {
     const int k = ch * kc + kv * 8;
 #pragma unroll
@@ -229,17 +254,17 @@ __device__ __noinline__ void consume_gemv(Ring& rg, const MegaArgs& A, const Meg
       }
     }
   };
-  for (int g0 = lo; g0 < hi; g0 += MG_G) {
-    const int nc = min(MG_G, hi - g0);
+  int grp_idx = 0;
+  for (int g0 = lo; g0 < hi; g0 += G) {
+    const int nc = min(G, hi - g0);
 #pragma unroll
-    for (int j = 0; j < MG_GP; ++j)
+    for (int m = 0; m < NACC; ++m)
 #pragma unroll
-      for (int r = 0; r < NR; ++r) acc[j][r] = 0.f;
+      for (int r = 0; r < NR; ++r) acc[m][r] = 0.f;
     for (int ch = 0; ch < n_chunks; ++ch) {
-      // ---- stage x[r][8] for this thread's K-slice (only when the slice changes: first group, or multi-chunk K);
-      //      with a multi-chunk K the next chunk's loads are issued before this chunk's math (software prefetch)
+      // ---- x[r][8] of this thread's K-slice: loaded once per phase (single-chunk K) or per chunk with the next
+      //      chunk's loads already in flight (multi-chunk K, never with LayerNorm)
       if (g0 == lo || n_chunks > 1) {
-        const int k = ch * kc + kv * 8;
         if (n_chunks == 1 || ch == 0) {
           load_x(xv, ch);
         } else {
@@ -249,138 +274,144 @@ __device__ __noinline__ void consume_gemv(Ring& rg, const MegaArgs& A, const Meg
             for (int i = 0; i < 8; ++i) xv[r][i] = xn[r][i];
         }
         if (n_chunks > 1) load_x(xn, (ch + 1) % n_chunks);
-        if (ln) {  // LayerNorm over the CTA (K <= 1536: single chunk): one reduction round for sum and sum of squares
-          float gg[8], bb[8];
-          if (active) {  // parameter loads in flight while the statistics are reduced
-            const float4 g0v = __ldg(reinterpret_cast<const float4*>(g.ln_g + k)), g1v = __ldg(reinterpret_cast<const float4*>(g.ln_g + k + 4));
-            const float4 b0v = __ldg(reinterpret_cast<const float4*>(g.ln_b + k)), b1v = __ldg(reinterpret_cast<const float4*>(g.ln_b + k + 4));
-            gg[0] = g0v.x; gg[1] = g0v.y; gg[2] = g0v.z; gg[3] = g0v.w; gg[4] = g1v.x; gg[5] = g1v.y; gg[6] = g1v.z; gg[7] = g1v.w;
-            bb[0] = b0v.x; bb[1] = b0v.y; bb[2] = b0v.z; bb[3] = b0v.w; bb[4] = b1v.x; bb[5] = b1v.y; bb[6] = b1v.z; bb[7] = b1v.w;
-          }
+        if (ln && active) {
+          const int k = ch * kc + kv * 8;
+          const float4 g0v = __ldg(reinterpret_cast<const float4*>(g.ln_g + k)), g1v = __ldg(reinterpret_cast<const float4*>(g.ln_g + k + 4));
+          const float gg[8] = {g0v.x, g0v.y, g0v.z, g0v.w, g1v.x, g1v.y, g1v.z, g1v.w};
 #pragma unroll
-          for (int r = 0; r < NR; ++r) {
-            float s1 = 0.f, s2 = 0.f;
-            if (part == 0)
+          for (int r = 0; r < NR; ++r)
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                s1 += xv[r][i];
-                s2 = fmaf(xv[r][i], xv[r][i], s2);
+            for (int i = 0; i < 8; ++i) {
+              if (part == 0) {
+                sx[r] += xv[r][i];
+                sxx[r] = fmaf(xv[r][i], xv[r][i], sxx[r]);
               }
-            s1 = warp_sum(s1);
-            s2 = warp_sum(s2);
-            if (lane == 0) {
-              s_stat[warp * 16 + r] = s1;
-              s_stat[warp * 16 + 8 + r] = s2;
+              xv[r][i] *= gg[i];
             }
-          }
-          cons_sync();
-          if (active) {
-#pragma unroll
-            for (int r = 0; r < NR; ++r) {
-              float t1 = 0.f, t2 = 0.f;
-              for (int w = 0; w < wpp; ++w) {
-                t1 += s_stat[w * 16 + r];
-                t2 += s_stat[w * 16 + 8 + r];
-              }
-              const float mean = t1 / g.K;
-              const float rstd = rsqrtf(fmaxf(t2 / g.K - mean * mean, 0.f) + 1e-5f);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) xv[r][i] = (xv[r][i] - mean) * rstd * gg[i] + bb[i];
-            }
-          }
-          cons_sync();  // s_stat reusable
         }
       }
       // ---- weights of this unit from the ring
       trace_ev(A, ctid, s_tr, 2);
-      const int st = rg.unit % MG_NSTAGE;
-      mbar_wait(rg.full(st), (rg.unit / MG_NSTAGE) & 1u);
+      const int st = unit % MG_NSTAGE;
+      mbar_wait(ring_full0 + 8u * st, (unit / MG_NSTAGE) & 1u);
       trace_ev(A, ctid, s_tr, 3);
       if (active) {
-        const uint8_t* stage = rg.data + st * MG_STAGE_BYTES;
+        const uint32_t stage = ring_data0 + st * MG_STAGE_BYTES;  // shared-space address: ld.shared, not generic loads
+        // two columns at a time, k-element outermost: 2 * NR independent FMA chains are interleaved so the 4-cycle FMA
+        // latency is covered by a single warp per scheduler (row-outer order left 8-deep dependent chains: 4x slower)
 #pragma unroll
-        for (int j = 0; j < MG_GP; ++j) {
-          const int cj = part + n_parts * j;
-          if (cj < nc) {
-            const uint4 u4 = *reinterpret_cast<const uint4*>(stage + cj * kc * 2 + kv * 16);
-            const __half2* h2 = reinterpret_cast<const __half2*>(&u4);
-            float wf[8];
+        for (int m = 0; m < NACC; m += 2) {
+          const int c0 = part + n_parts * m, c1 = part + n_parts * (m + 1);
+          if (c0 < nc) {
+            const bool two = c1 < nc;
+            const uint4 ua = lds128(stage + c0 * kc * 2 + kv * 16);
+            const uint4 ub = two ? lds128(stage + c1 * kc * 2 + kv * 16) : make_uint4(0u, 0u, 0u, 0u);
+            const __half2* ha = reinterpret_cast<const __half2*>(&ua);
+            const __half2* hb = reinterpret_cast<const __half2*>(&ub);
+            float wa[8], wb[8];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float2 f = __half22float2(h2[i]);
-              wf[2 * i] = f.x;
-              wf[2 * i + 1] = f.y;
+              const float2 fa = __half22float2(ha[i]), fb = __half22float2(hb[i]);
+              wa[2 * i] = fa.x; wa[2 * i + 1] = fa.y;
+              wb[2 * i] = fb.x; wb[2 * i + 1] = fb.y;
             }
 #pragma unroll
-            for (int r = 0; r < NR; ++r)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
-              for (int i = 0; i < 8; ++i) acc[j][r] = fmaf(xv[r][i], wf[i], acc[j][r]);
+              for (int r = 0; r < NR; ++r) {
+                acc[m][r] = fmaf(xv[r][i], wa[i], acc[m][r]);
+                acc[m + 1][r] = fmaf(xv[r][i], wb[i], acc[m + 1][r]);
+              }
           }
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(rg.empty(st));
-      ++rg.unit;
+      if (lane == 0) mbar_arrive(ring_empty0 + 8u * st);
+      ++unit;
     }
-    // ---- group done: reduce over the K-slices (lanes, then the warps of the part) and write the outputs
+    // ---- group done: reduce over the K-slices (lanes by a transposing shuffle network, warps through smem)
     trace_ev(A, ctid, s_tr, 4);
+    float* sr = s_red + (grp_idx & 1) * (NSET * MG_CONS_WARPS * 32);  // double buffered: one barrier per group
     float red[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) red[i] = 0.f;
+    for (int set = 0; set < NSET; ++set) {
 #pragma unroll
-    for (int j = 0; j < MG_GP; ++j)
+      for (int i = 0; i < 32; ++i) red[i] = 0.f;
 #pragma unroll
-      for (int r = 0; r < NR; ++r) red[j * NR + r] = acc[j][r];
-    const float tot = warp_transpose_reduce32(red, lane);
-    float* sr = s_red + (grp_idx & 1) * (MG_CONS_WARPS * 32);  // double buffered: one barrier per group
+      for (int j = 0; j < GP; ++j)
+#pragma unroll
+        for (int r = 0; r < NR; ++r) red[j * NR + r] = acc[set * GP + j][r];
+      sr[(set * MG_CONS_WARPS + warp) * 32 + lane] = warp_transpose_reduce32(red, lane);
+    }
+    if (ln && grp_idx == 0) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) red[i] = 0.f;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        red[r] = sx[r];
+        red[16 + r] = sxx[r];
+      }
+      s_lnred[warp * 32 + lane] = warp_transpose_reduce32(red, lane);
+    }
     ++grp_idx;
-    sr[warp * 32 + lane] = tot;
     trace_ev(A, ctid, s_tr, 5);
     cons_sync();
     trace_ev(A, ctid, s_tr, 6);
     // the last two consumer warps finish the outputs (with d_model >= 1280 they hold no K-slice, so this overlaps the
-    // other warps' next group; s_red is double buffered and the next cons_sync orders the reuse)
+    // other warps' next group; the reduction buffer is double buffered and the next cons_sync orders its reuse)
     if (ctid >= MG_CONS - 64) {
-      const int et = ctid - (MG_CONS - 64);
-      const int p = et >> 5, i = et & 31;
-      const int j = i / NR, r = i - j * NR;
-      const int cj = p + n_parts * j;
-      if (p < n_parts && j < MG_GP && cj < nc && r < R) {
-        float v = 0.f;
-        for (int w = 0; w < wpp; ++w) v += sr[(p * wpp + w) * 32 + i];
-        const int n = g0 + cj;
-        if (g.bias != nullptr) v += bias_smem ? s_bias[n - lo] : __ldg(g.bias + n);
-        switch (g.epi) {
-          case GV_STORE:
-            g.out[static_cast<long long>(r) * g.ldo + n] = v;
-            break;
-          case GV_RESID: {  // residual columns are owned by this CTA for the whole pass: no global read-modify-write
-            const float nv = s_xown[r * 16 + (n - lo)] + v;
-            s_xown[r * 16 + (n - lo)] = nv;
-            g.out[static_cast<long long>(r) * g.ldo + n] = nv;
-            break;
-          }
-          case GV_GELU:
-            g.out[static_cast<long long>(r) * g.ldo + n] = gelu_erf(v);
-            break;
-          case GV_QKV: {
-            const int d = A.d;
-            if (n < d) {
-              g.out[static_cast<long long>(r) * g.ldo + n] = v;
-            } else {
-              const int pos = A.st->pos;
-              __half* cache = (n < 2 * d) ? ly->kcache : ly->vcache;
-              const int e = (n < 2 * d) ? n - d : n - 2 * d;
-              cache[(static_cast<long long>(r) * A.t_max + pos) * d + e] = __float2half_rn(v);
+      for (int idx = ctid - (MG_CONS - 64); idx < n_parts * NSET * 32; idx += 64) {
+        const int p = idx / (NSET * 32), set = (idx >> 5) % NSET, i = idx & 31;
+        const int j = i / NR, r = i - j * NR;
+        const int cj = p + n_parts * (set * GP + j);
+        if (j < GP && cj < nc && r < R) {
+          float v = 0.f;
+          for (int w = 0; w < wpp; ++w) v += sr[(set * MG_CONS_WARPS + p * wpp + w) * 32 + i];
+          const int n = g0 + cj;
+          if (ln) {
+            float t1 = 0.f, t2 = 0.f;
+            for (int w = 0; w < wpp; ++w) {
+              t1 += s_lnred[w * 32 + r];
+              t2 += s_lnred[w * 32 + 16 + r];
             }
-            break;
+            const float mean = t1 / g.K;
+            const float rstd = rsqrtf(fmaxf(t2 / g.K - mean * mean, 0.f) + 1e-5f);
+            v = rstd * (v - mean * (pre ? s_s2[n - lo] : __ldg(g.ln_s2 + n)));
           }
-          default:
-            break;
+          v += pre ? s_bias[n - lo] : (g.bias != nullptr ? __ldg(g.bias + n) : 0.f);
+          switch (g.epi) {
+            case GV_STORE:
+              g.out[static_cast<long long>(r) * g.ldo + n] = v;
+              break;
+            case GV_RESID: {  // residual columns are owned by this CTA for the whole pass: no global read-modify-write
+              const float nv = s_xown[r * 16 + (n - lo)] + v;
+              s_xown[r * 16 + (n - lo)] = nv;
+              g.out[static_cast<long long>(r) * g.ldo + n] = nv;
+              break;
+            }
+            case GV_GELU:
+              g.out[static_cast<long long>(r) * g.ldo + n] = gelu_erf(v);
+              break;
+            case GV_QKV: {
+              const int d = A.d;
+              if (n < d) {
+                g.out[static_cast<long long>(r) * g.ldo + n] = v;
+              } else {
+                const int pos = A.st->pos;
+                __half* cache = (n < 2 * d) ? ly->kcache : ly->vcache;
+                const int e = (n < 2 * d) ? n - d : n - 2 * d;
+                cache[(static_cast<long long>(r) * A.t_max + pos) * d + e] = __float2half_rn(v);
+              }
+              break;
+            }
+            default:
+              break;
+          }
         }
       }
     }
   }
+  rg.unit = unit;
 }
 
 // ------------------------------------------------------------------ consumer: self-attention phase
@@ -451,40 +482,40 @@ __device__ __noinline__ void consume_self_attn(const MegaArgs& A, const MegaLaye
 }
 
 // ------------------------------------------------------------------ consumer: cross-attention phase
-// task = (utterance, head, key split); K and V chunks arrive through the ring; 40 groups of 8 lanes walk the keys with
-// an online softmax for all beams at once, merged through shared memory into one partial (acc[64], m, l) per beam.
+// 28 groups of 8 lanes walk the split's keys with an online softmax for all beams at once (K/V are read once for every
+// beam); groups are merged by shuffles (4 per warp) and shared memory into one partial (acc[64], m, l) per beam; the
+// last split of a head to arrive (atomic counter) merges the S partials into ctx.
 template <int NB>
 __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid, float* s_part, int* s_flag) {
-  const CrossGeom cg = cross_geom(A.n_utt, A.H);
   const int grp = ctid >> 3, gl = ctid & 7;
-  constexpr int NGRP = MG_CONS / 8;  // 40
-  const int d = A.d, beam = A.beam;
+  constexpr int NGRP = MG_CONS / 8;  // 28
+  const int d = A.d, beam = A.beam, H = A.H;
+  const float* qbase = A.q;
+  float* ctx = A.ctx;
+  float* cross_part = A.cross_part;
+  unsigned* cross_count = A.cross_count;
+  const uint32_t ring_data0 = rg.data0, ring_full0 = rg.full0, ring_empty0 = rg.empty0;
+  unsigned unit = rg.unit;
   const unsigned gmask = 0xFFu << (ctid & 24);
+  const CrossGeom cg = cross_geom(A.n_utt, H);
   for (int task = blockIdx.x; task < cg.n_tasks; task += gridDim.x) {
     const int split = task % cg.S, uh = task / cg.S;
-    const int u = uh / A.H, h = uh - u * A.H;
+    const int u = uh / H, h = uh - u * H;
     const int t0 = split * cg.KS;
-    const int nk = min(cg.KS, T_ENC_PAD - t0);
+    int nk = min(cg.KS, T_ENC - t0);  // keys >= 1500 (padding rows) are never touched
+    if (nk < 0) nk = 0;
     float qv[NB][8];
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) qv[k][i] = 0.f;
       if (k < beam) {
-        const float* qr = A.q + static_cast<long long>(u * beam + k) * d + h * HEAD_DIM + gl * 8;
+        const float* qr = qbase + static_cast<long long>(u * beam + k) * d + h * HEAD_DIM + gl * 8;
         const float4 a0 = ldcg_f4(qr), a1 = ldcg_f4(qr + 4);
-        qv[k][0] = a0.x; qv[k][1] = a0.y; qv[k][2] = a0.z; qv[k][3] = a0.w;
-        qv[k][4] = a1.x; qv[k][5] = a1.y; qv[k][6] = a1.z; qv[k][7] = a1.w;
+        qv[k][0] = a0.x * 0.125f; qv[k][1] = a0.y * 0.125f; qv[k][2] = a0.z * 0.125f; qv[k][3] = a0.w * 0.125f;
+        qv[k][4] = a1.x * 0.125f; qv[k][5] = a1.y * 0.125f; qv[k][6] = a1.z * 0.125f; qv[k][7] = a1.w * 0.125f;
       }
     }
-    const int stK = rg.unit % MG_NSTAGE;
-    const unsigned phK = (rg.unit / MG_NSTAGE) & 1u;
-    const int stV = (rg.unit + 1) % MG_NSTAGE;
-    const unsigned phV = ((rg.unit + 1) / MG_NSTAGE) & 1u;
-    mbar_wait(rg.full(stK), phK);
-    mbar_wait(rg.full(stV), phV);
-    const __half* sK = reinterpret_cast<const __half*>(rg.data + stK * MG_STAGE_BYTES);
-    const __half* sV = reinterpret_cast<const __half*>(rg.data + stV * MG_STAGE_BYTES);
     float m[NB], l[NB], acc[NB][8];
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
@@ -493,11 +524,14 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
     }
+    const int stK = unit % MG_NSTAGE, stV = (unit + 1) % MG_NSTAGE;
+    mbar_wait(ring_full0 + 8u * stK, (unit / MG_NSTAGE) & 1u);
+    mbar_wait(ring_full0 + 8u * stV, ((unit + 1) / MG_NSTAGE) & 1u);
+    const uint32_t sK = ring_data0 + stK * MG_STAGE_BYTES, sV = ring_data0 + stV * MG_STAGE_BYTES;
 #pragma unroll 1
     for (int tl = grp; tl < nk; tl += NGRP) {
-      if (t0 + tl >= T_ENC) break;
-      const uint4 ku = *reinterpret_cast<const uint4*>(sK + tl * HEAD_DIM + gl * 8);
-      const uint4 vu = *reinterpret_cast<const uint4*>(sV + tl * HEAD_DIM + gl * 8);
+      const uint4 ku = lds128(sK + tl * (HEAD_DIM * 2) + gl * 16);
+      const uint4 vu = lds128(sV + tl * (HEAD_DIM * 2) + gl * 16);
       float kf[8], vf[8];
       {
         const __half2* k2 = reinterpret_cast<const __half2*>(&ku);
@@ -509,17 +543,21 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
           vf[2 * i] = b.x; vf[2 * i + 1] = b.y;
         }
       }
+      float sc[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k) sc[k] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int k = 0; k < NB; ++k) sc[k] = fmaf(qv[k][i], kf[i], sc[k]);
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s = fmaf(qv[k][i], kf[i], s);
-        s += __shfl_xor_sync(gmask, s, 1);
-        s += __shfl_xor_sync(gmask, s, 2);
-        s += __shfl_xor_sync(gmask, s, 4);
-        s *= 0.125f;
-        const float mn = fmaxf(m[k], s);
-        const float al = __expf(m[k] - mn), p = __expf(s - mn);
+        float sk = sc[k];
+        sk += __shfl_xor_sync(gmask, sk, 1);
+        sk += __shfl_xor_sync(gmask, sk, 2);
+        sk += __shfl_xor_sync(gmask, sk, 4);
+        const float mn = fmaxf(m[k], sk);
+        const float al = __expf(m[k] - mn), p = __expf(sk - mn);
         l[k] = l[k] * al + p;
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[k][i] = fmaf(acc[k][i], al, p * vf[i]);
@@ -528,12 +566,11 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
     }
     __syncwarp();
     if ((ctid & 31) == 0) {
-      mbar_arrive(rg.empty(stK));
-      mbar_arrive(rg.empty(stV));
+      mbar_arrive(ring_empty0 + 8u * stK);
+      mbar_arrive(ring_empty0 + 8u * stV);
     }
-    rg.unit += 2;
-    // merge: first the 4 groups of a warp with shuffles (lanes l, l^8, l^16 hold the same dims), then the 10 warps
-    // through shared memory: s_part[warp][k][66]
+    unit += 2;
+    // merge: the 4 groups of a warp with shuffles (lanes l, l^8, l^16 hold the same dims), then the warps through smem
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
 #pragma unroll
@@ -573,7 +610,7 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
         a = fmaf(w, s_part[(g * NB + k) * 66 + e], a);
         ll = fmaf(w, s_part[(g * NB + k) * 66 + 65], ll);
       }
-      float* out = A.cross_part + (static_cast<long long>(uh) * cg.S + split) * (MAX_BEAM * 68) + k * 68;
+      float* out = cross_part + (static_cast<long long>(uh) * cg.S + split) * (MAX_BEAM * 68) + k * 68;
       out[e] = a;
       if (e == 0) {
         out[64] = mm;
@@ -584,16 +621,16 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
     __threadfence();
     cons_sync();
     if (ctid == 0) {
-      const unsigned prev = atomicAdd(A.cross_count + uh, 1u);
+      const unsigned prev = atomicAdd(cross_count + uh, 1u);
       s_flag[0] = (prev == static_cast<unsigned>(cg.S - 1)) ? 1 : 0;
-      if (s_flag[0]) A.cross_count[uh] = 0;  // reset for the next layer (ordered by the grid barriers)
+      if (s_flag[0]) cross_count[uh] = 0;  // reset for the next layer (ordered by the grid barriers)
     }
     cons_sync();
     if (s_flag[0]) {
       __threadfence();
       for (int idx = ctid; idx < beam * HEAD_DIM; idx += MG_CONS) {
         const int k = idx / HEAD_DIM, e = idx - k * HEAD_DIM;
-        const float* pb = A.cross_part + (static_cast<long long>(uh) * cg.S) * (MAX_BEAM * 68) + k * 68;
+        const float* pb = cross_part + (static_cast<long long>(uh) * cg.S) * (MAX_BEAM * 68) + k * 68;
         float mm = -INFINITY;
         for (int s2 = 0; s2 < cg.S; ++s2) mm = fmaxf(mm, ldcg_f(pb + s2 * (MAX_BEAM * 68) + 64));
         float a = 0.f, ll = 0.f;
@@ -603,11 +640,12 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
           a = fmaf(w, ldcg_f(pb + s2 * (MAX_BEAM * 68) + e), a);
           ll = fmaf(w, ldcg_f(pb + s2 * (MAX_BEAM * 68) + 65), ll);
         }
-        A.ctx[static_cast<long long>(u * beam + k) * d + h * HEAD_DIM + e] = a / ll;
+        ctx[static_cast<long long>(u * beam + k) * d + h * HEAD_DIM + e] = a / ll;
       }
     }
     cons_sync();
   }
+  rg.unit = unit;
 }
 
 template <int NR>
@@ -616,8 +654,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs 
   uint8_t* ring_data = mg_smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(mg_smem + MG_NSTAGE * MG_STAGE_BYTES);
   float* s_red = reinterpret_cast<float*>(mg_smem + MG_NSTAGE * MG_STAGE_BYTES + 1024);
-  float* s_stat = s_red + 2 * MG_CONS_WARPS * 32;
-  float* s_part = s_stat + 1024;  // [40][NB][66] for the cross-attention merge; also self-attention scratch
+  float* s_stat = s_red + MG_RED_FLOATS;  // 1056 floats: [0,256) unused, bias, s2, own residual columns, flags
+  float* s_part = s_stat + 1056;  // [40][NB][66] for the cross-attention merge; also self-attention scratch
   Ring rg;
   rg.data = ring_data;
   rg.data0 = smem_u32(ring_data);
@@ -640,15 +678,15 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs 
     if (tid == MG_CONS) {
       for (int l = 0; l < L; ++l) {
         const MegaLayer& ly = A.layers[l];
-        produce_gemv(rg, ly.qkv, mg_gp(NR));
-        produce_gemv(rg, ly.o, mg_gp(NR));
-        produce_gemv(rg, ly.cq, mg_gp(NR));
+        produce_gemv(rg, ly.qkv, mg_gp(NR) * mg_nset(NR));
+        produce_gemv(rg, ly.o, mg_gp(NR) * mg_nset(NR));
+        produce_gemv(rg, ly.cq, mg_gp(NR) * mg_nset(NR));
         produce_cross(rg, A, ly);
-        produce_gemv(rg, ly.co, mg_gp(NR));
-        produce_gemv(rg, ly.fc1, mg_gp(NR));
-        produce_gemv(rg, ly.fc2, mg_gp(NR));
+        produce_gemv(rg, ly.co, mg_gp(NR) * mg_nset(NR));
+        produce_gemv(rg, ly.fc1, mg_gp(NR) * mg_nset(NR));
+        produce_gemv(rg, ly.fc2, mg_gp(NR) * mg_nset(NR));
       }
-      if (A.with_logits) produce_gemv(rg, A.vocab, mg_gp(NR));
+      if (A.with_logits) produce_gemv(rg, A.vocab, mg_gp(NR) * mg_nset(NR));
     }
     return;
   }
@@ -675,24 +713,24 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs 
   grid_barrier(A, epoch, ctid, epoch0);
   for (int l = 0; l < L; ++l) {
     const MegaLayer& ly = A.layers[l];
-    consume_gemv<NR>(rg, A, ly.qkv, &ly, ctid, s_red, s_stat, s_part);
+    consume_gemv<NR>(rg, A, ly.qkv, &ly, ctid, s_red, s_stat);
     grid_barrier(A, epoch, ctid, epoch0);
     consume_self_attn(A, ly, ctid, s_part, reinterpret_cast<unsigned short*>(s_part + MG_CONS_WARPS * 448));
     grid_barrier(A, epoch, ctid, epoch0);
-    consume_gemv<NR>(rg, A, ly.o, &ly, ctid, s_red, s_stat, s_part);
+    consume_gemv<NR>(rg, A, ly.o, &ly, ctid, s_red, s_stat);
     grid_barrier(A, epoch, ctid, epoch0);
-    consume_gemv<NR>(rg, A, ly.cq, &ly, ctid, s_red, s_stat, s_part);
+    consume_gemv<NR>(rg, A, ly.cq, &ly, ctid, s_red, s_stat);
     grid_barrier(A, epoch, ctid, epoch0);
     consume_cross<NR>(rg, A, ctid, s_part, reinterpret_cast<int*>(s_stat + 1000));  // beam <= rows <= NR
     grid_barrier(A, epoch, ctid, epoch0);
-    consume_gemv<NR>(rg, A, ly.co, &ly, ctid, s_red, s_stat, s_part);
+    consume_gemv<NR>(rg, A, ly.co, &ly, ctid, s_red, s_stat);
     grid_barrier(A, epoch, ctid, epoch0);
-    consume_gemv<NR>(rg, A, ly.fc1, &ly, ctid, s_red, s_stat, s_part);
+    consume_gemv<NR>(rg, A, ly.fc1, &ly, ctid, s_red, s_stat);
     grid_barrier(A, epoch, ctid, epoch0);
-    consume_gemv<NR>(rg, A, ly.fc2, &ly, ctid, s_red, s_stat, s_part);
+    consume_gemv<NR>(rg, A, ly.fc2, &ly, ctid, s_red, s_stat);
     grid_barrier(A, epoch, ctid, epoch0);
   }
-  if (A.with_logits) consume_gemv<NR>(rg, A, A.vocab, nullptr, ctid, s_red, s_stat, s_part);
+  if (A.with_logits) consume_gemv<NR>(rg, A, A.vocab, nullptr, ctid, s_red, s_stat);
   // publish the final epoch for the next launch (every CTA leaves the same value behind)
   grid_barrier(A, epoch, ctid, epoch0);
   if (blockIdx.x == 0 && ctid == 0) *A.epoch_base = epoch;
@@ -710,6 +748,31 @@ __global__ void chunk_major_kernel(const __half* __restrict__ src, __half* __res
 }
 
 }  // namespace
+
+__global__ void ln_fold_kernel(const __half* __restrict__ w, const float* __restrict__ g, const float* __restrict__ b,
+                               const float* __restrict__ bias, float* __restrict__ s2, float* __restrict__ biasf, int N, int K) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float a = 0.f, c = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = __half2float(w[static_cast<long long>(n) * K + k]);
+    a = fmaf(g[k], wv, a);
+    c = fmaf(b[k], wv, c);
+  }
+  a = warp_sum(a);
+  c = warp_sum(c);
+  if (lane == 0) {
+    s2[n] = a;
+    biasf[n] = c + (bias != nullptr ? bias[n] : 0.f);
+  }
+}
+
+void mega_ln_fold(const __half* w, const float* g, const float* b, const float* bias, float* s2, float* biasf, int N, int K,
+                  cudaStream_t stream) {
+  ln_fold_kernel<<<cdiv(N, 8), 256, 0, stream>>>(w, g, b, bias, s2, biasf, N, K);
+  WISB_CUDA(cudaGetLastError());
+}
 
 int mega_k_chunks(int K) {
   int n = (K + MG_KC_MAX - 1) / MG_KC_MAX;

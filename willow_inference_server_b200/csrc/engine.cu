@@ -137,6 +137,7 @@ struct wisb_handle {
   DevBuf<unsigned> mega_flags;
   DevBuf<float> cross_part;
   DevBuf<unsigned> cross_count;
+  DevBuf<float> ln_fold;       // per LN-GEMV: s2[N] and folded bias[N] (qkv, cq, fc1 of every decoder layer, vocab)
   DevBuf<__half> fc2_chunked;  // decoder fc2 weights in chunk-major layout for the persistent pass kernel
   DevBuf<unsigned long long> mega_trace;
   int mega_trace_on = 0;
@@ -307,6 +308,22 @@ void finish_create(wisb_handle* h) {
   h->mega_layers_host.ensure(d.n_dec_layers);
   h->mega_flags.ensure(mega_flags_words(), true);
   h->cross_count.ensure(static_cast<size_t>(DEC_MAX_ROWS) * d.n_heads, true);
+  {
+    // LayerNorm fold vectors for the persistent pass kernel (decoder_mega.cu consume_gemv)
+    const size_t per_layer = 2ull * (3 * d.d_model + d.d_model + 4 * d.d_model);
+    h->ln_fold.ensure(per_layer * d.n_dec_layers + 2ull * d.n_vocab_pad);
+    for (int i = 0; i < d.n_dec_layers; ++i) {
+      const DecLayerW& w = h->dec_w[i];
+      float* base = h->ln_fold.p + per_layer * i;
+      mega_ln_fold(w.qkvw, w.ln1g, w.ln1b, w.qkvb, base, base + 3 * d.d_model, 3 * d.d_model, d.d_model, h->stream);
+      base += 6 * d.d_model;
+      mega_ln_fold(w.cqw, w.ln2g, w.ln2b, w.cqb, base, base + d.d_model, d.d_model, d.d_model, h->stream);
+      base += 2 * d.d_model;
+      mega_ln_fold(w.fc1w, w.ln3g, w.ln3b, w.fc1b, base, base + 4 * d.d_model, 4 * d.d_model, d.d_model, h->stream);
+    }
+    float* vb = h->ln_fold.p + per_layer * d.n_dec_layers;
+    mega_ln_fold(h->H("dec.tok_emb"), h->F("dec.ln.g"), h->F("dec.ln.b"), nullptr, vb, vb + d.n_vocab_pad, d.n_vocab, d.d_model, h->stream);
+  }
   if (mega_k_chunks(4 * d.d_model) > 1) {
     const size_t per = static_cast<size_t>(4) * d.d_model * d.d_model;
     h->fc2_chunked.ensure(per * d.n_dec_layers);
@@ -523,15 +540,18 @@ void upload_mega_layers(wisb_handle* h, const DecodeCfg& c) {
     const DecLayerW& w = h->dec_w[i];
     MegaLayer& m = h->mega_layers_host.p[i];
     m = MegaLayer();
-    auto set = [&](MegaGemv& g, const __half* wt, const float* bias, const float* lg, const float* lb, const float* x,
+    // (LayerNorm-fused GEMVs: `bias` is the folded bias, ln_s2 the fold vector, both precomputed at load)
+    auto set = [&](MegaGemv& g, const __half* wt, const float* bias, const float* lg, const float* s2, const float* x,
                    float* out, long long ldo, int N, int K, int epi) {
-      g.w = wt; g.bias = bias; g.ln_g = lg; g.ln_b = lb; g.x = x; g.out = out; g.ldo = ldo; g.N = N; g.K = K; g.epi = epi;
+      g.w = wt; g.bias = bias; g.ln_g = lg; g.ln_s2 = s2; g.x = x; g.out = out; g.ldo = ldo; g.N = N; g.K = K; g.epi = epi;
     };
-    set(m.qkv, w.qkvw, w.qkvb, w.ln1g, w.ln1b, h->dx.p, h->dq.p, d, 3 * d, d, GV_QKV);
+    const size_t per_layer = 2ull * (3 * d + d + 4 * d);
+    const float* fb = h->ln_fold.p + per_layer * i;
+    set(m.qkv, w.qkvw, fb + 3 * d, w.ln1g, fb, h->dx.p, h->dq.p, d, 3 * d, d, GV_QKV);
     set(m.o, w.ow, w.ob, nullptr, nullptr, h->dctx.p, h->dx.p, d, d, d, GV_RESID);
-    set(m.cq, w.cqw, w.cqb, w.ln2g, w.ln2b, h->dx.p, h->dq.p, d, d, d, GV_STORE);
+    set(m.cq, w.cqw, fb + 7 * d, w.ln2g, fb + 6 * d, h->dx.p, h->dq.p, d, d, d, GV_STORE);
     set(m.co, w.cow, w.cob, nullptr, nullptr, h->dctx.p, h->dx.p, d, d, d, GV_RESID);
-    set(m.fc1, w.fc1w, w.fc1b, w.ln3g, w.ln3b, h->dx.p, h->dh.p, 4 * d, 4 * d, d, GV_GELU);
+    set(m.fc1, w.fc1w, fb + 12 * d, w.ln3g, fb + 8 * d, h->dx.p, h->dh.p, 4 * d, 4 * d, d, GV_GELU);
     const __half* fc2w = h->fc2_chunked.p ? h->fc2_chunked.p + static_cast<size_t>(4) * d * d * i : w.fc2w;
     set(m.fc2, fc2w, w.fc2b, nullptr, nullptr, h->dh.p, h->dx.p, d, d, 4 * d, GV_RESID);
     m.ck = h->ckv.p + (static_cast<size_t>(i * 2 + 0) * c.B_total + c.u0) * head_block;
@@ -550,7 +570,12 @@ int enqueue_decoder_forward_mega(wisb_handle* h, const DecodeCfg& c, bool with_l
   a.n_layers = dm.n_dec_layers;
   a.vocab.w = h->H("dec.tok_emb");
   a.vocab.ln_g = h->F("dec.ln.g");
-  a.vocab.ln_b = h->F("dec.ln.b");
+  {
+    const size_t per_layer = 2ull * 8 * dm.d_model;
+    const float* vb = h->ln_fold.p + per_layer * dm.n_dec_layers;
+    a.vocab.ln_s2 = vb;
+    a.vocab.bias = vb + dm.n_vocab_pad;
+  }
   a.vocab.x = h->dx.p;
   a.vocab.out = h->logits.p;
   a.vocab.ldo = dm.n_vocab_pad;
