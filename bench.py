@@ -44,12 +44,38 @@ PROMPT = [50258, 50259, 50359, 50363]
 SEED = 0
 
 
+def synth_utterance(n_samples: int, seed: int = 1234) -> np.ndarray:
+    """SURVEY.md section 8(d) input recipe: 0.3 sin(2 pi (200 + 300 t) t) + 0.05 N(0,1), 16 kHz mono float32."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n_samples, dtype=np.float64) / 16000.0
+    return (0.3 * np.sin(2.0 * np.pi * (200.0 + 300.0 * t) * t) + 0.05 * rng.standard_normal(n_samples)).astype(np.float32)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
         return d, "measured (MEASURED_PEAKS.json)"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+def gemm_dram_traffic_per_launch():
+    """dram__bytes_read + dram__bytes_write per gemm_tc_kernel launch from the committed ncu --set full capture
+    (profiles/r01_gemm_tc_full.csv), averaged over the captured launches; None if the summary is missing."""
+    import csv
+
+    p = os.path.join(ROOT, "profiles", "r01_gemm_tc_full.csv")
+    if not os.path.exists(p):
+        return None
+    rows = list(csv.reader(open(p)))
+    hdr, units = rows[0], rows[1]
+    try:
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    except ValueError:
+        return None
+    scale = {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Gbyte": 1e9}
+    tot = [float(r[ir]) * scale.get(units[ir], 1e6) + float(r[iw]) * scale.get(units[iw], 1e6) for r in rows[2:]]
+    return int(sum(tot) / len(tot)) if tot else None
 
 
 def encoder_gemm_flops(dims, windows=1):
@@ -120,7 +146,6 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from oracle import logmel as om  # synthetic input recipe only; not on the timed path
     from willow_inference_server_b200 import _lib, audio, models, weights as W
 
     rank = int(os.environ.get("RANK", "0"))
@@ -132,29 +157,23 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dims = W.WhisperDims.for_size(MODEL)
     # ---- load: rank 0 builds the blob, everyone receives it over NCCL (the only collective in the system)
+    from willow_inference_server_b200 import parallel
+
     t0 = time.time()
     if rank == 0:
         host, tensors = make_blob_host(dims)
-        nbytes = torch.tensor([host.numel()], dtype=torch.int64, device="cuda")
     else:
-        host, tensors, nbytes = None, None, torch.zeros(1, dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.broadcast(nbytes, 0)
-    blob_dev = torch.empty(int(nbytes.item()), dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        blob_dev.copy_(host, non_blocking=False)
-    t_bcast = None
-    if world > 1:
-        torch.cuda.synchronize()
-        tb = time.time()
-        dist.broadcast(blob_dev, 0)
-        torch.cuda.synchronize()
-        t_bcast = time.time() - tb
+        host, tensors = torch.empty(0, dtype=torch.uint8), None
+    torch.cuda.synchronize()
+    tb = time.time()
+    blob_dev = parallel.broadcast_blob(host, torch.device("cuda", local))
+    torch.cuda.synchronize()
+    t_bcast = (time.time() - tb) if world > 1 else None
     handle = _lib.Handle.from_device(blob_dev.data_ptr(), blob_dev.numel(), local, keepalive=blob_dev)
     load_s = time.time() - t0
     os.environ["WISB_DEVICE"] = str(local)
 
-    pcm = om.synth_utterance(AUDIO_SAMPLES, seed=1234 + rank)
+    pcm = synth_utterance(AUDIO_SAMPLES, seed=1234 + rank)
     pcm_dev = torch.from_numpy(pcm).cuda()
     prompts = np.array([PROMPT], np.int32)
     off, ns = np.zeros(1, np.int64), np.array([AUDIO_SAMPLES], np.int32)
@@ -261,7 +280,9 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, encoder + cross-K/V GEMMs)",
                      "achieved": round(gemm_tf, 1) if gemm_tf else None, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": round(gemm_tf / peak_tf, 4) if gemm_tf else None, "traffic": None,
+                     "frac": round(gemm_tf / peak_tf, 4) if gemm_tf else None, "traffic": gemm_dram_traffic_per_launch(),
+                     "traffic_note": "bytes per launch, mean of the ncu --set full capture in profiles/r01_gemm_tc_full.csv "
+                                     "(algorithmic operand bytes of those launches: 13.7-21.0 MB)",
                      "peak_source": pk_src + " bf16_tflops_sustained (kernel timed inside a long step)",
                      "algorithmic_flops_per_step": flops, "launches_per_step": n_gemm,
                      "avg_launch_ms": round(prof["gemm_ms"] / n_gemm, 4) if prof.get("gemm_ms") else None,

@@ -7,11 +7,10 @@ sys.path.insert(0, ROOT)
 import bench
 from willow_inference_server_b200 import _lib, weights as W
 import torch
-from oracle import logmel as om
 dims = W.WhisperDims.for_size("large-v2")
 host, _ = bench.make_blob_host(dims)
 h = _lib.Handle.from_host(host.numpy(), 0)
-pcm = torch.from_numpy(om.synth_utterance(bench.AUDIO_SAMPLES, 1234)).cuda()
+pcm = torch.from_numpy(bench.synth_utterance(bench.AUDIO_SAMPLES, 1234)).cuda()
 off, ns = np.zeros(1, np.int64), np.array([bench.AUDIO_SAMPLES], np.int32)
 prompts = np.array([bench.PROMPT], np.int32)
 h.set_option("mega_trace", 1)

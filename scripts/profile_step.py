@@ -31,9 +31,8 @@ host, _ = bench.make_blob_host(dims)
 h = _lib.Handle.from_host(host.numpy(), 0)
 if args.no_graphs:
     h.set_option("use_graphs", 0)
-from oracle import logmel as om  # noqa: E402
 
-pcm = torch.from_numpy(om.synth_utterance(bench.AUDIO_SAMPLES, 1234)).cuda()
+pcm = torch.from_numpy(bench.synth_utterance(bench.AUDIO_SAMPLES, 1234)).cuda()
 off, ns = np.zeros(1, np.int64), np.array([bench.AUDIO_SAMPLES], np.int32)
 prompts = np.array([bench.PROMPT], np.int32)
 for i in range(args.warmup + args.steps):
