@@ -258,7 +258,7 @@ def run_ours(args):
     e2e_value = world * AUDIO_SECONDS * args.steps / wall_e2e
     dec_bytes = 2 * (16 * dims.n_dec_layers * dims.d_model ** 2 + dims.n_vocab * dims.d_model) + \
         4 * dims.n_dec_layers * 1500 * dims.d_model
-    steps_per = 3 + N_OUT
+    steps_per = int(t["decode_steps"])  # decoder passes per utterance (prompt prefix in one pass + N_OUT search steps)
     out = {
         "metric": "Whisper large-v2 realtime multiple (audio s / s), beam 5, 3.84 s utterance",
         "value": round(value, 2), "unit": "x realtime", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -89,7 +89,7 @@ void search_step_run(const SearchArgs& a, cudaStream_t stream);
 // prompt prefill: no search, just feed the next prompt token and advance the position
 void prefill_advance_run(int* tokens, const int* prompt /*[n_utt][prompt_len]*/, int prompt_len, int R, int beam,
                          DecState* st, cudaStream_t stream);
-void search_init_run(const SearchArgs& a, const int* prompt, cudaStream_t stream);
+void search_init_run(const SearchArgs& a, const int* prompt, cudaStream_t stream, int shared_prefix = 0);
 
 // ------------------------------------------------------------------ persistent decoder pass (decoder_mega.cu)
 struct MegaGemv {
@@ -115,6 +115,9 @@ struct MegaArgs {
   MegaGemv vocab;
   int with_logits = 0;
   int R = 0, d = 0, H = 0, n_utt = 0, beam = 0, t_max = 0;
+  // prompt prefill in one pass: rows = n_utt x pf_len prompt positions (beam := pf_len for the cross-attention phase),
+  // tokens -> prompt [n_utt][pf_tok_stride], K/V written to cache slot u * pf_slot_stride; 0 = normal decoding step
+  int pf_len = 0, pf_tok_stride = 0, pf_slot_stride = 0;
   const int* tokens = nullptr;
   const __half* tok_emb = nullptr;
   const float* pos_emb = nullptr;

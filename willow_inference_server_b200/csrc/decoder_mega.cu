@@ -69,6 +69,15 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lan
   return v[0];
 }
 
+// Row geometry.  Normal step: every row is at position st->pos and owns cache slot r.  Prompt prefill (pf_len > 0): the
+// pass carries the first pf_len prompt positions of each utterance as rows (utterance-major), all written into the cache
+// slot of the utterance's first beam, so the whole prompt prefix costs ONE pass instead of pf_len passes.
+__device__ __forceinline__ int row_pos(const MegaArgs& A, int r) { return A.pf_len > 0 ? r % A.pf_len : A.st->pos; }
+__device__ __forceinline__ int row_slot(const MegaArgs& A, int r) { return A.pf_len > 0 ? (r / A.pf_len) * A.pf_slot_stride : r; }
+__device__ __forceinline__ int row_token(const MegaArgs& A, int r) {
+  return A.pf_len > 0 ? A.tokens[(r / A.pf_len) * A.pf_tok_stride + (r % A.pf_len)] : A.tokens[r];
+}
+
 struct Ring {
   uint32_t full0, empty0, data0;  // shared-memory addresses
   uint8_t* data;
@@ -397,10 +406,10 @@ __device__ __noinline__ void consume_gemv(Ring& rg, const MegaArgs& A, const Meg
               if (n < d) {
                 g.out[static_cast<long long>(r) * g.ldo + n] = v;
               } else {
-                const int pos = A.st->pos;
+                const int pos = row_pos(A, r);
                 __half* cache = (n < 2 * d) ? ly->kcache : ly->vcache;
                 const int e = (n < 2 * d) ? n - d : n - 2 * d;
-                cache[(static_cast<long long>(r) * A.t_max + pos) * d + e] = __float2half_rn(v);
+                cache[(static_cast<long long>(row_slot(A, r)) * A.t_max + pos) * d + e] = __float2half_rn(v);
               }
               break;
             }
@@ -419,12 +428,14 @@ __device__ __noinline__ void consume_gemv(Ring& rg, const MegaArgs& A, const Meg
 __device__ __noinline__ void consume_self_attn(const MegaArgs& A, const MegaLayer& ly, int ctid, float* s_p, unsigned short* s_slot) {
   const int lane = ctid & 31, warp = ctid >> 5;
   const int d = A.d, H = A.H;
-  const int pos = A.st->pos;
   const int n_tasks = A.R * H;
   for (int base = blockIdx.x * MG_CONS_WARPS; base < n_tasks; base += gridDim.x * MG_CONS_WARPS) {
     const int task = base + warp;
     if (task < n_tasks) {
       const int r = task / H, h = task - r * H;
+      const int pos = row_pos(A, r);
+      const int own = row_slot(A, r);
+      const bool pf = A.pf_len > 0;
       const int* indir = (*A.flip ? A.indir1 : A.indir0) + static_cast<long long>(r) * A.t_max;
       const float* qr = A.q + static_cast<long long>(r) * d + h * HEAD_DIM;
       float* sp = s_p + warp * 448;
@@ -437,7 +448,7 @@ __device__ __noinline__ void consume_self_attn(const MegaArgs& A, const MegaLaye
       }
       float mx = -INFINITY;
       for (int t = lane; t <= pos; t += 32) {
-        const int slot = (t == pos) ? r : indir[t];
+        const int slot = (pf || t == pos) ? own : indir[t];
         ss[t] = static_cast<unsigned short>(slot);
         const uint4* kr = reinterpret_cast<const uint4*>(ly.kcache + (static_cast<long long>(slot) * A.t_max + t) * d + h * HEAD_DIM);
         float s = 0.f;
@@ -698,14 +709,13 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs 
   if (A.trace != nullptr && blockIdx.x == 0 && ctid == 0) A.trace[0] = globaltimer_ns();
   // phase 0: token + positional embedding; every CTA produces (and keeps) the residual-stream columns it owns
   {
-    const int pos = A.st->pos;
     int lo, hi;
     cta_cols(A.d, lo, hi);
     float* s_xown = s_stat + 768;
     for (int idx = ctid; idx < A.R * (hi - lo); idx += MG_CONS) {
       const int r = idx / (hi - lo), c = idx - r * (hi - lo);
-      const float v = __half2float(A.tok_emb[static_cast<long long>(A.tokens[r]) * A.d + lo + c]) +
-                      A.pos_emb[static_cast<long long>(pos) * A.d + lo + c];
+      const float v = __half2float(A.tok_emb[static_cast<long long>(row_token(A, r)) * A.d + lo + c]) +
+                      A.pos_emb[static_cast<long long>(row_pos(A, r)) * A.d + lo + c];
       s_xown[r * 16 + c] = v;
       A.x[static_cast<long long>(r) * A.d + lo + c] = v;
     }

@@ -563,7 +563,7 @@ void upload_mega_layers(wisb_handle* h, const DecodeCfg& c) {
                             cudaMemcpyHostToDevice, h->stream));
 }
 
-int enqueue_decoder_forward_mega(wisb_handle* h, const DecodeCfg& c, bool with_logits) {
+int enqueue_decoder_forward_mega(wisb_handle* h, const DecodeCfg& c, bool with_logits, bool prefill_pass = false) {
   const Dims& dm = h->dims;
   MegaArgs a;
   a.layers = h->mega_layers.p;
@@ -590,6 +590,14 @@ int enqueue_decoder_forward_mega(wisb_handle* h, const DecodeCfg& c, bool with_l
   a.beam = c.beam;
   a.t_max = T_MAX;
   a.tokens = h->tokens.p;
+  if (prefill_pass) {  // the whole prompt prefix of every utterance in ONE pass (rows = utterances x prefix positions)
+    a.pf_len = c.prompt_len - 1;
+    a.pf_tok_stride = c.prompt_len;
+    a.pf_slot_stride = c.beam;
+    a.R = c.n_utt * a.pf_len;
+    a.beam = a.pf_len;
+    a.tokens = h->prompt_dev.p;
+  }
   a.tok_emb = h->H("dec.tok_emb");
   a.pos_emb = h->F("dec.pos");
   a.x = h->dx.p;
@@ -740,14 +748,22 @@ int decode_pass(wisb_handle* h, const DecodeCfg& c, const int32_t* prompts, int3
   memcpy(h->pin_i.p + 4, prompts + static_cast<size_t>(c.u0) * c.prompt_len, sizeof(int) * c.n_utt * c.prompt_len);
   WISB_CUDA(cudaMemcpyAsync(h->prompt_dev.p, h->pin_i.p + 4, sizeof(int) * c.n_utt * c.prompt_len, cudaMemcpyHostToDevice, s));
   SearchArgs sa = make_search_args(h, c);
-  search_init_run(sa, h->prompt_dev.p, s);
+  // persistent-pass path: forward the prompt prefix of all utterances in one pass when it fits the 8-row kernel
+  const int pf_rows = c.n_utt * (c.prompt_len - 1);
+  const bool one_pass_prefill = h->decoder_mega && c.prompt_len > 1 && pf_rows <= DEC_MAX_ROWS && c.prompt_len - 1 <= MAX_BEAM;
+  search_init_run(sa, h->prompt_dev.p, s, one_pass_prefill ? 1 : 0);
   if (h->decoder_mega) upload_mega_layers(h, c);
   if (c.max_new > 0) {
     // the persistent pass kernel is a handful of launches per step: no graph needed (and it is a cooperative launch)
     DecGraphs* g = (h->use_graphs && !h->decoder_mega) ? &get_graphs(h, c) : nullptr;
-    for (int p = 0; p + 1 < c.prompt_len; ++p) {
-      if (g) WISB_CUDA(cudaGraphLaunch(g->prefill, s)); else enqueue_prefill(h, c);
+    if (one_pass_prefill) {
+      enqueue_decoder_forward_mega(h, c, false, true);
       ++steps;
+    } else {
+      for (int p = 0; p + 1 < c.prompt_len; ++p) {
+        if (g) WISB_CUDA(cudaGraphLaunch(g->prefill, s)); else enqueue_prefill(h, c);
+        ++steps;
+      }
     }
     const int fwd = h->decoder_mega ? 1 : 1 + 8 * h->dims.n_dec_layers + 1;
     const int per_step = fwd + 4;

@@ -288,18 +288,21 @@ __global__ void prefill_advance_kernel(int* tokens, const int* prompt, int promp
   if (threadIdx.x == 0) st->pos = next;
 }
 
-__global__ void search_init_kernel(const SearchArgs a, const int* prompt) {
+// shared_prefix: the prompt prefix (all but the last prompt token) is forwarded once per utterance into the cache slot of
+// its first beam by a single prefill pass; decoding then starts at the last prompt token and every beam's indirection
+// points at that slot.
+__global__ void search_init_kernel(const SearchArgs a, const int* prompt, int shared_prefix) {
   const int R = a.n_utt * a.beam;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, n = gridDim.x * blockDim.x;
   if (tid == 0) {
-    a.st->pos = 0;
+    a.st->pos = shared_prefix ? a.prompt_len - 1 : 0;
     a.st->gen_step = 0;
     a.st->n_done = 0;
     a.st->all_done = 0;
     *a.flip = 0;
   }
   for (int i = tid; i < R; i += n) {
-    a.tokens[i] = prompt[(i / a.beam) * a.prompt_len];
+    a.tokens[i] = prompt[(i / a.beam) * a.prompt_len + (shared_prefix ? a.prompt_len - 1 : 0)];
     a.cum[i] = 0.f;
   }
   for (int i = tid; i < a.n_utt; i += n) {
@@ -309,8 +312,10 @@ __global__ void search_init_kernel(const SearchArgs a, const int* prompt) {
     a.best_len[i] = 0;
   }
   for (int i = tid; i < R * a.t_max; i += n) {
-    a.indir[0][i] = i / a.t_max;  // identity: every row holds its own copy of the prompt prefix
-    a.indir[1][i] = i / a.t_max;
+    const int r = i / a.t_max;
+    const int slot = shared_prefix ? (r / a.beam) * a.beam : r;  // else identity: every row holds its own prefix copy
+    a.indir[0][i] = slot;
+    a.indir[1][i] = slot;
   }
 }
 
@@ -350,8 +355,8 @@ void prefill_advance_run(int* tokens, const int* prompt, int prompt_len, int R, 
   WISB_CUDA(cudaGetLastError());
 }
 
-void search_init_run(const SearchArgs& a, const int* prompt, cudaStream_t stream) {
-  search_init_kernel<<<8, 256, 0, stream>>>(a, prompt);
+void search_init_run(const SearchArgs& a, const int* prompt, cudaStream_t stream, int shared_prefix) {
+  search_init_kernel<<<8, 256, 0, stream>>>(a, prompt, shared_prefix);
   WISB_CUDA(cudaGetLastError());
 }
 
