@@ -43,6 +43,15 @@ def test_gemm_structured_inputs_catch_layout_bugs(h):
         assert np.array_equal(c, w.astype(np.float32)[:, np.arange(M) % K].T)
 
 
+def test_multicast_cluster_variant_is_bit_identical(h):
+    # 2-CTA clusters with TMA-multicast W tiles vs the single-CTA kernel: same MMAs, same order -> identical bits
+    rng = np.random.default_rng(3)
+    for M, N, K, bn in [(256, 256, 128, 128), (512, 512, 640, 256), (1536, 3840, 1280, 256), (1536, 1280, 5120, 128)]:
+        a = rng.standard_normal((M, K), dtype=np.float32).astype(np.float16)
+        w = rng.standard_normal((N, K), dtype=np.float32).astype(np.float16)
+        assert np.array_equal(h.debug_gemm(a, w, impl=0, bn=bn), h.debug_gemm(a, w, impl=0, bn=-bn))
+
+
 def test_simt_crosscheck_agrees(h):
     rng = np.random.default_rng(1)
     a = rng.standard_normal((256, 256), dtype=np.float32).astype(np.float16)

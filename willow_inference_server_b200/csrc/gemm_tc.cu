@@ -142,7 +142,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, int row, int co
   }
 }
 
-template <int BN>
+// kMC: launched as clusters of 2 CTAs that own vertically adjacent M tiles of the same N tile; each CTA fetches half of
+// the W tile and TMA-multicasts it to both, which cuts the L2->SM operand traffic per MMA from (128+BN) to (128+BN/2) rows
+// (the 1-CTA kernel is L2-feed limited at ~50 % of the tensor peak).  MMAs stay cta_group::1.
+template <int BN, bool kMC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N, int K,
                int a_wrap, const GemmEpi epi) {
@@ -166,13 +169,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const int m_tiles = M / BM;
   const int n_tiles = (N + BN - 1) / BN;
-  const int total_tiles = m_tiles * n_tiles;
   const int k_blocks = K / BK;
+  // work items: single tiles, or (kMC) vertical tile pairs handled by a 2-CTA cluster (rank r takes M tile 2 * pair + r)
+  const uint32_t crank = kMC ? cluster_ctarank() : 0u;
+  const int m_units = kMC ? m_tiles / 2 : m_tiles;
+  const int total_tiles = m_units * n_tiles;
+  const int first_unit = kMC ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int unit_stride = kMC ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  auto unit_m0 = [&](int unit) { return ((unit % m_units) * (kMC ? 2 : 1) + static_cast<int>(crank)) * BM; };
+  auto unit_n0 = [&](int unit) { return (unit / m_units) * BN; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), kMC ? 2 : 1);  // kMC: the stage is free once BOTH CTAs' MMAs have consumed it
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -188,6 +198,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (kMC) cluster_sync_all();  // peer barriers are initialised before any multicast copy / remote commit can arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -196,9 +207,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile % m_tiles) * BM;
-        const int n0 = (tile / m_tiles) * BN;
+      for (int tile = first_unit; tile < total_tiles; tile += unit_stride) {
+        const int m0 = unit_m0(tile);
+        const int n0 = unit_n0(tile);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
@@ -209,7 +220,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             ra += 1;
           }
           tma_load_2d(smem_a0 + stage * A_STAGE_BYTES, &map_a, full_bar(stage), ka, ra);
-          tma_load_2d(smem_b0 + stage * Cfg::B_STAGE_BYTES, &map_b, full_bar(stage), kb * BK, n0);
+          if (kMC) {  // my half of the W tile, delivered to both CTAs (the peer delivers the other half)
+            tma_load_2d_mcast(smem_b0 + stage * Cfg::B_STAGE_BYTES + crank * (Cfg::B_STAGE_BYTES / 2), &map_b, full_bar(stage),
+                              kb * BK, n0 + static_cast<int>(crank) * (BN / 2), 0x3);
+          } else {
+            tma_load_2d(smem_b0 + stage * Cfg::B_STAGE_BYTES, &map_b, full_bar(stage), kb * BK, n0);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -224,7 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = first_unit; tile < total_tiles; tile += unit_stride, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1u;
         mbar_wait(tempty_bar(as), aphase ^ 1u);
@@ -240,7 +256,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // advance 16 fp16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
             umma_f16_ss(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));  // frees this smem stage once the MMAs above have read it
+          // frees this smem stage once the MMAs above have read it (kMC: in both CTAs, the peer multicasts into it too)
+          if (kMC) umma_commit_mcast(empty_bar(stage), 0x3); else umma_commit(empty_bar(stage));
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -253,11 +270,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_unit; tile < total_tiles; tile += unit_stride, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1u;
-      const int m0 = (tile % m_tiles) * BM;
-      const int n0 = (tile / m_tiles) * BN;
+      const int m0 = unit_m0(tile);
+      const int n0 = unit_n0(tile);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
@@ -278,6 +295,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (kMC) cluster_sync_all();  // the peer may still be multicasting into / committing onto this CTA's shared memory
   if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
@@ -339,7 +357,8 @@ void gemm_plan(GemmPlan& p, const __half* a, long long lda, const __half* w, int
   p.epi = epi;
   if (p.epi.m_valid <= 0) p.epi.m_valid = M;
   if (p.epi.n_valid <= 0) p.epi.n_valid = N;
-  int bn = force_bn;
+  const bool no_mcast = force_bn < 0;
+  int bn = force_bn < 0 ? -force_bn : force_bn;
   if (bn == 0) {
     // 256-wide tiles halve the A re-reads; use them when they still give every SM work
     const int tiles256 = (M / BM) * ((N + 255) / 256);
@@ -348,7 +367,14 @@ void gemm_plan(GemmPlan& p, const __half* a, long long lda, const __half* w, int
   WISB_REQUIRE(bn == 128 || bn == 256, "gemm: BN must be 128 or 256");
   p.BN = bn;
   const int tiles = (M / BM) * ((N + bn - 1) / bn);
-  p.grid = tiles < num_sms ? tiles : num_sms;
+  // 2-CTA clusters with multicast W tiles whenever the M tiles pair up and N tiles are whole
+  p.mcast = (!no_mcast && (M / BM) % 2 == 0 && N % bn == 0 && a_wrap == 0 && num_sms >= 2) ? 1 : 0;
+  if (p.mcast) {
+    const int units = tiles / 2, clusters = num_sms / 2;
+    p.grid = 2 * (units < clusters ? units : clusters);
+  } else {
+    p.grid = tiles < num_sms ? tiles : num_sms;
+  }
   p.a_wrap = a_wrap;
   if (a_wrap > 0) {
     WISB_REQUIRE(a_wrap % BK == 0 && lda == a_wrap && K > a_wrap && K - a_wrap <= a_wrap, "gemm: bad a_wrap");
@@ -356,21 +382,36 @@ void gemm_plan(GemmPlan& p, const __half* a, long long lda, const __half* w, int
   } else {
     make_tmap_f16_2d(&p.map_a, a, K, M, lda, BK, BM);
   }
-  make_tmap_f16_2d(&p.map_b, w, K, N, K, BK, bn);
+  make_tmap_f16_2d(&p.map_b, w, K, N, K, BK, p.mcast ? bn / 2 : bn);
+}
+
+template <int BN, bool kMC>
+void gemm_launch(const GemmPlan& p, cudaStream_t stream) {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    WISB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, kMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
+  });
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = GemmCfg<BN>::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kMC ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  WISB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, kMC>, p.map_a, p.map_b, p.M, p.N, p.K, p.a_wrap, p.epi));
 }
 
 void gemm_run(const GemmPlan& p, cudaStream_t stream) {
-  static std::once_flag once;
-  std::call_once(once, [] {
-    WISB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::SMEM_BYTES));
-    WISB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::SMEM_BYTES));
-  });
   if (p.BN == 256) {
-    gemm_tc_kernel<256><<<p.grid, GEMM_THREADS, GemmCfg<256>::SMEM_BYTES, stream>>>(p.map_a, p.map_b, p.M, p.N, p.K, p.a_wrap, p.epi);
+    if (p.mcast) gemm_launch<256, true>(p, stream); else gemm_launch<256, false>(p, stream);
   } else {
-    gemm_tc_kernel<128><<<p.grid, GEMM_THREADS, GemmCfg<128>::SMEM_BYTES, stream>>>(p.map_a, p.map_b, p.M, p.N, p.K, p.a_wrap, p.epi);
+    if (p.mcast) gemm_launch<128, true>(p, stream); else gemm_launch<128, false>(p, stream);
   }
-  WISB_CUDA(cudaGetLastError());
 }
 
 void gemm_ref_run(const __half* a, long long lda, const __half* w, float* c, int M, int N, int K, cudaStream_t stream) {

@@ -30,7 +30,7 @@ struct GemmEpi {
 
 struct GemmPlan {
   CUtensorMap map_a, map_b;
-  int M = 0, N = 0, K = 0, BN = 128, grid = 0, a_wrap = 0;
+  int M = 0, N = 0, K = 0, BN = 128, grid = 0, a_wrap = 0, mcast = 0;
   GemmEpi epi;
 };
 
@@ -38,6 +38,7 @@ struct GemmPlan {
 // a_wrap > 0 (conv2): A is stored as rows of `a_wrap` (= lda) elements and logical row r continues into row r + 1.
 void gemm_plan(GemmPlan& p, const __half* a, long long lda, const __half* w, int M, int N, int K, const GemmEpi& epi,
                int num_sms, int force_bn = 0, int a_wrap = 0);
+// (force_bn < 0: same |force_bn| tile but without the 2-CTA multicast clusters -- diagnostics)
 void gemm_run(const GemmPlan& p, cudaStream_t stream);
 // slow SIMT cross-check used only by the diagnostics entry point / tests
 void gemm_ref_run(const __half* a, long long lda, const __half* w, float* c, int M, int N, int K, cudaStream_t stream);
