@@ -15,7 +15,7 @@ def h():
 
 @pytest.mark.parametrize("M,N,K,bn", [
     (128, 128, 64, 128), (128, 256, 128, 256), (256, 384, 320, 128), (1536, 1280, 1280, 0),
-    (384, 640, 3840, 256), (128, 51968, 128, 0), (2048, 5120, 1280, 256),
+    (384, 640, 3840, 256), (128, 51968, 128, 0), (2048, 5120, 1280, 256), (1536, 3840, 1280, 160), (256, 320, 192, 160),
 ])
 def test_gemm_matches_fp32(h, M, N, K, bn):
     rng = np.random.default_rng(M * 7 + N * 3 + K)
@@ -46,7 +46,8 @@ def test_gemm_structured_inputs_catch_layout_bugs(h):
 def test_multicast_cluster_variant_is_bit_identical(h):
     # 2-CTA clusters with TMA-multicast W tiles vs the single-CTA kernel: same MMAs, same order -> identical bits
     rng = np.random.default_rng(3)
-    for M, N, K, bn in [(256, 256, 128, 128), (512, 512, 640, 256), (1536, 3840, 1280, 256), (1536, 1280, 5120, 128)]:
+    for M, N, K, bn in [(256, 256, 128, 128), (512, 512, 640, 256), (1536, 3840, 1280, 256), (1536, 1280, 5120, 128),
+                        (1536, 3840, 1280, 160)]:
         a = rng.standard_normal((M, K), dtype=np.float32).astype(np.float16)
         w = rng.standard_normal((N, K), dtype=np.float32).astype(np.float16)
         assert np.array_equal(h.debug_gemm(a, w, impl=0, bn=bn), h.debug_gemm(a, w, impl=0, bn=-bn))

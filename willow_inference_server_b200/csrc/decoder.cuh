@@ -129,7 +129,7 @@ struct MegaArgs {
   const int* flip = nullptr;
   const DecState* st = nullptr;
   float* cross_part = nullptr;   // [n_utt][H][S<=16][MAX_BEAM][68] (64 acc, m, l, pad)
-  unsigned* cross_count = nullptr;  // [n_utt * H] arrival counters of the key splits (zero between layers)
+  unsigned* cross_flags = nullptr;  // [n_utt * H][16] epoch-tagged 'partial written' flags, one 128-byte line each
   unsigned* flags = nullptr;     // grid-barrier epoch flags, one 128-byte line per CTA
   unsigned* epoch_base = nullptr;
   unsigned long long* trace = nullptr;  // optional: [2*k] = time phase k starts, [2*k+1] = time CTA 0 reached barrier k

@@ -497,14 +497,13 @@ __device__ __noinline__ void consume_self_attn(const MegaArgs& A, const MegaLaye
 // beam); groups are merged by shuffles (4 per warp) and shared memory into one partial (acc[64], m, l) per beam; the
 // last split of a head to arrive (atomic counter) merges the S partials into ctx.
 template <int NB>
-__device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid, float* s_part, int* s_flag) {
+__device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid, float* s_part, unsigned tag) {
   const int grp = ctid >> 3, gl = ctid & 7;
   constexpr int NGRP = MG_CONS / 8;  // 28
   const int d = A.d, beam = A.beam, H = A.H;
   const float* qbase = A.q;
   float* ctx = A.ctx;
   float* cross_part = A.cross_part;
-  unsigned* cross_count = A.cross_count;
   const uint32_t ring_data0 = rg.data0, ring_full0 = rg.full0, ring_empty0 = rg.empty0;
   unsigned unit = rg.unit;
   const unsigned gmask = 0xFFu << (ctid & 24);
@@ -628,17 +627,18 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
         out[65] = ll;
       }
     }
-    // split-K style fix-up: the last split of (utterance, head) to arrive merges all partials into ctx
-    __threadfence();
+    // split-K fix-up without atomics or fences on the critical path: every split publishes an epoch-tagged flag (release
+    // store by one thread after the CTA barrier); split 0 of the head polls the S flags (acquire) and merges the partials.
+    // All other CTAs go straight on to the grid barrier.
     cons_sync();
-    if (ctid == 0) {
-      const unsigned prev = atomicAdd(cross_count + uh, 1u);
-      s_flag[0] = (prev == static_cast<unsigned>(cg.S - 1)) ? 1 : 0;
-      if (s_flag[0]) cross_count[uh] = 0;  // reset for the next layer (ordered by the grid barriers)
-    }
-    cons_sync();
-    if (s_flag[0]) {
-      __threadfence();
+    if (ctid == 0) st_release_gpu(A.cross_flags + (uh * 16 + split) * 32, tag);
+    if (split == 0) {
+      if (ctid < cg.S) {
+        const unsigned* f = A.cross_flags + (uh * 16 + ctid) * 32;
+        while (ld_acquire_gpu(f) != tag) {
+        }
+      }
+      cons_sync();
       for (int idx = ctid; idx < beam * HEAD_DIM; idx += MG_CONS) {
         const int k = idx / HEAD_DIM, e = idx - k * HEAD_DIM;
         const float* pb = cross_part + (static_cast<long long>(uh) * cg.S) * (MAX_BEAM * 68) + k * 68;
@@ -731,7 +731,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs 
     grid_barrier(A, epoch, ctid, epoch0);
     consume_gemv<NR>(rg, A, ly.cq, &ly, ctid, s_red, s_stat);
     grid_barrier(A, epoch, ctid, epoch0);
-    consume_cross<NR>(rg, A, ctid, s_part, reinterpret_cast<int*>(s_stat + 1000));  // beam <= rows <= NR
+    consume_cross<NR>(rg, A, ctid, s_part, epoch + 1);  // beam <= rows <= NR; tag = a value unique to this phase
     grid_barrier(A, epoch, ctid, epoch0);
     consume_gemv<NR>(rg, A, ly.co, &ly, ctid, s_red, s_stat);
     grid_barrier(A, epoch, ctid, epoch0);

@@ -136,7 +136,7 @@ struct wisb_handle {
   DevBuf<MegaLayer> mega_layers;
   DevBuf<unsigned> mega_flags;
   DevBuf<float> cross_part;
-  DevBuf<unsigned> cross_count;
+  DevBuf<unsigned> cross_flags;
   DevBuf<float> ln_fold;       // per LN-GEMV: s2[N] and folded bias[N] (qkv, cq, fc1 of every decoder layer, vocab)
   DevBuf<__half> fc2_chunked;  // decoder fc2 weights in chunk-major layout for the persistent pass kernel
   DevBuf<unsigned long long> mega_trace;
@@ -307,7 +307,7 @@ void finish_create(wisb_handle* h) {
   h->mega_layers.ensure(d.n_dec_layers);
   h->mega_layers_host.ensure(d.n_dec_layers);
   h->mega_flags.ensure(mega_flags_words(), true);
-  h->cross_count.ensure(static_cast<size_t>(DEC_MAX_ROWS) * d.n_heads, true);
+  h->cross_flags.ensure(static_cast<size_t>(DEC_MAX_ROWS) * d.n_heads * 16 * 32, true);
   {
     // LayerNorm fold vectors for the persistent pass kernel (decoder_mega.cu consume_gemv)
     const size_t per_layer = 2ull * (3 * d.d_model + d.d_model + 4 * d.d_model);
@@ -608,7 +608,7 @@ int enqueue_decoder_forward_mega(wisb_handle* h, const DecodeCfg& c, bool with_l
   a.flip = h->flip.p;
   a.st = h->st.p;
   a.cross_part = h->cross_part.p;
-  a.cross_count = h->cross_count.p;
+  a.cross_flags = h->cross_flags.p;
   a.flags = h->mega_flags.p;
   a.epoch_base = h->mega_flags.p + 160 * 32;
   if (h->mega_trace_on) {

@@ -26,9 +26,9 @@ constexpr int GEMM_THREADS = 192;
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 160 ? 5 : 6);
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;  // power of two >= two accumulator buffers
   static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -360,11 +360,21 @@ void gemm_plan(GemmPlan& p, const __half* a, long long lda, const __half* w, int
   const bool no_mcast = force_bn < 0;
   int bn = force_bn < 0 ? -force_bn : force_bn;
   if (bn == 0) {
-    // 256-wide tiles halve the A re-reads; use them when they still give every SM work
-    const int tiles256 = (M / BM) * ((N + 255) / 256);
-    bn = (N % 256 == 0 && tiles256 >= num_sms) ? 256 : 128;
+    // wave quantisation on `num_sms` CTAs dominates at one window (M = 1536): pick the tile width with the fewest
+    // (waves x tile cost); e.g. N = 3840 -> 160 (288 tiles = 1.95 waves) instead of 256 (180 tiles = 1.22 -> 2 waves)
+    long long best = -1;
+    for (int cand : {256, 160, 128}) {
+      if (N % cand != 0) continue;
+      const long long t = static_cast<long long>(M / BM) * (N / cand);
+      const long long cost = ((t + num_sms - 1) / num_sms) * (cand + 48);
+      if (best < 0 || cost < best) {
+        best = cost;
+        bn = cand;
+      }
+    }
+    if (bn == 0) bn = 128;
   }
-  WISB_REQUIRE(bn == 128 || bn == 256, "gemm: BN must be 128 or 256");
+  WISB_REQUIRE(bn == 128 || bn == 160 || bn == 256, "gemm: BN must be 128, 160 or 256");
   p.BN = bn;
   const int tiles = (M / BM) * ((N + bn - 1) / bn);
   // 2-CTA clusters with multicast W tiles whenever the M tiles pair up and N tiles are whole
@@ -409,6 +419,8 @@ void gemm_launch(const GemmPlan& p, cudaStream_t stream) {
 void gemm_run(const GemmPlan& p, cudaStream_t stream) {
   if (p.BN == 256) {
     if (p.mcast) gemm_launch<256, true>(p, stream); else gemm_launch<256, false>(p, stream);
+  } else if (p.BN == 160) {
+    if (p.mcast) gemm_launch<160, true>(p, stream); else gemm_launch<160, false>(p, stream);
   } else {
     if (p.mcast) gemm_launch<128, true>(p, stream); else gemm_launch<128, false>(p, stream);
   }
