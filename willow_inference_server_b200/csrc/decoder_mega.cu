@@ -44,6 +44,7 @@ __host__ __device__ constexpr int mg_nset(int nr) { return nr <= 5 ? 2 : 1; }
 
 __device__ __forceinline__ float ldcg_f(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ float4 ldcg_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float2 ldcg_f2(const float* p) { return __ldcg(reinterpret_cast<const float2*>(p)); }
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
@@ -233,12 +234,12 @@ __device__ __noinline__ void consume_gemv(Ring& rg, const MegaArgs& A, const Meg
   const bool ln = g.ln_s2 != nullptr;
   int* s_tr = reinterpret_cast<int*>(s_stat + 1001);
   trace_ev(A, ctid, s_tr, 1);
-  float* s_bias = s_stat + 256;        // [<=256] bias (LN: folded bias) of this CTA's columns
-  float* s_s2 = s_stat + 512;          // [<=256] LN fold vector of this CTA's columns
-  float* s_xown = s_stat + 768;        // [8][16] residual-stream columns owned by this CTA (kept across phases)
+  float* s_bias = s_stat + 16;         // [<=384] bias (LN: folded bias) of this CTA's columns
+  float* s_s2 = s_stat + 400;          // [<=384] LN fold vector of this CTA's columns
+  float* s_xown = s_stat + 784;        // [8][16] residual-stream columns owned by this CTA (kept across phases)
   float* s_lnred = s_red + 2 * NSET * MG_CONS_WARPS * 32;  // [warps][32] per-warp partial row sums (LN)
   const int ncols = hi - lo;
-  const bool pre = ncols <= 256;
+  const bool pre = ncols <= 384;  // the vocabulary projection has 351 columns per CTA
   if (pre) {
     for (int i = ctid; i < ncols; i += MG_CONS) {
       s_bias[i] = g.bias != nullptr ? __ldg(g.bias + lo + i) : 0.f;
@@ -508,6 +509,8 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
   unsigned unit = rg.unit;
   const unsigned gmask = 0xFFu << (ctid & 24);
   const CrossGeom cg = cross_geom(A.n_utt, H);
+  int* s_tr = reinterpret_cast<int*>(s_part) - 55;  // = s_stat + 1001 (trace cursor)
+  trace_ev(A, ctid, s_tr, 10);
   for (int task = blockIdx.x; task < cg.n_tasks; task += gridDim.x) {
     const int split = task % cg.S, uh = task / cg.S;
     const int u = uh / H, h = uh - u * H;
@@ -534,46 +537,67 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
     }
+    trace_ev(A, ctid, s_tr, 11);
     const int stK = unit % MG_NSTAGE, stV = (unit + 1) % MG_NSTAGE;
     mbar_wait(ring_full0 + 8u * stK, (unit / MG_NSTAGE) & 1u);
     mbar_wait(ring_full0 + 8u * stV, ((unit + 1) / MG_NSTAGE) & 1u);
     const uint32_t sK = ring_data0 + stK * MG_STAGE_BYTES, sV = ring_data0 + stV * MG_STAGE_BYTES;
+    trace_ev(A, ctid, s_tr, 12);
 #pragma unroll 1
-    for (int tl = grp; tl < nk; tl += NGRP) {
-      const uint4 ku = lds128(sK + tl * (HEAD_DIM * 2) + gl * 16);
-      const uint4 vu = lds128(sV + tl * (HEAD_DIM * 2) + gl * 16);
-      float kf[8], vf[8];
+    for (int tl = grp; tl < nk; tl += 2 * NGRP) {
+      // two keys per step with one joint running-max update: shorter dependency chains, 3 exps and 3 FMAs per pair
+      const bool hasb = tl + NGRP < nk;
+      const int tb = hasb ? tl + NGRP : tl;
+      const uint4 kua = lds128(sK + tl * (HEAD_DIM * 2) + gl * 16), kub = lds128(sK + tb * (HEAD_DIM * 2) + gl * 16);
+      const uint4 vua = lds128(sV + tl * (HEAD_DIM * 2) + gl * 16), vub = lds128(sV + tb * (HEAD_DIM * 2) + gl * 16);
+      float sa[NB], sb[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k) sa[k] = sb[k] = 0.f;
       {
-        const __half2* k2 = reinterpret_cast<const __half2*>(&ku);
-        const __half2* v2 = reinterpret_cast<const __half2*>(&vu);
+        const __half2* ka2 = reinterpret_cast<const __half2*>(&kua);
+        const __half2* kb2 = reinterpret_cast<const __half2*>(&kub);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float2 a = __half22float2(k2[i]), b = __half22float2(v2[i]);
-          kf[2 * i] = a.x; kf[2 * i + 1] = a.y;
-          vf[2 * i] = b.x; vf[2 * i + 1] = b.y;
+          const float2 fa = __half22float2(ka2[i]), fb = __half22float2(kb2[i]);
+#pragma unroll
+          for (int k = 0; k < NB; ++k) {
+            sa[k] = fmaf(qv[k][2 * i], fa.x, sa[k]);
+            sb[k] = fmaf(qv[k][2 * i], fb.x, sb[k]);
+            sa[k] = fmaf(qv[k][2 * i + 1], fa.y, sa[k]);
+            sb[k] = fmaf(qv[k][2 * i + 1], fb.y, sb[k]);
+          }
         }
       }
-      float sc[NB];
+      float vfa[8], vfb[8];
+      {
+        const __half2* va2 = reinterpret_cast<const __half2*>(&vua);
+        const __half2* vb2 = reinterpret_cast<const __half2*>(&vub);
 #pragma unroll
-      for (int k = 0; k < NB; ++k) sc[k] = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int k = 0; k < NB; ++k) sc[k] = fmaf(qv[k][i], kf[i], sc[k]);
+        for (int i = 0; i < 4; ++i) {
+          const float2 fa = __half22float2(va2[i]), fb = __half22float2(vb2[i]);
+          vfa[2 * i] = fa.x; vfa[2 * i + 1] = fa.y;
+          vfb[2 * i] = fb.x; vfb[2 * i + 1] = fb.y;
+        }
+      }
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
-        float sk = sc[k];
-        sk += __shfl_xor_sync(gmask, sk, 1);
-        sk += __shfl_xor_sync(gmask, sk, 2);
-        sk += __shfl_xor_sync(gmask, sk, 4);
-        const float mn = fmaxf(m[k], sk);
-        const float al = __expf(m[k] - mn), p = __expf(sk - mn);
-        l[k] = l[k] * al + p;
+        float xa = sa[k], xb = sb[k];
+        xa += __shfl_xor_sync(gmask, xa, 1);
+        xb += __shfl_xor_sync(gmask, xb, 1);
+        xa += __shfl_xor_sync(gmask, xa, 2);
+        xb += __shfl_xor_sync(gmask, xb, 2);
+        xa += __shfl_xor_sync(gmask, xa, 4);
+        xb += __shfl_xor_sync(gmask, xb, 4);
+        if (!hasb) xb = -INFINITY;
+        const float mn = fmaxf(m[k], fmaxf(xa, xb));
+        const float al = __expf(m[k] - mn), pa = __expf(xa - mn), pb = __expf(xb - mn);
+        l[k] = fmaf(l[k], al, pa + pb);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[k][i] = fmaf(acc[k][i], al, p * vf[i]);
+        for (int i = 0; i < 8; ++i) acc[k][i] = fmaf(acc[k][i], al, fmaf(pa, vfa[i], pb * vfb[i]));
         m[k] = mn;
       }
     }
+    trace_ev(A, ctid, s_tr, 13);
     __syncwarp();
     if ((ctid & 31) == 0) {
       mbar_arrive(ring_empty0 + 8u * stK);
@@ -608,6 +632,7 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
         }
       }
     }
+    trace_ev(A, ctid, s_tr, 14);
     cons_sync();
     for (int idx = ctid; idx < beam * HEAD_DIM; idx += MG_CONS) {
       const int k = idx / HEAD_DIM, e = idx - k * HEAD_DIM;
@@ -630,6 +655,7 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
     // split-K fix-up without atomics or fences on the critical path: every split publishes an epoch-tagged flag (release
     // store by one thread after the CTA barrier); split 0 of the head polls the S flags (acquire) and merges the partials.
     // All other CTAs go straight on to the grid barrier.
+    trace_ev(A, ctid, s_tr, 15);
     cons_sync();
     if (ctid == 0) st_release_gpu(A.cross_flags + (uh * 16 + split) * 32, tag);
     if (split == 0) {
@@ -638,22 +664,38 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
         while (ld_acquire_gpu(f) != tag) {
         }
       }
+      trace_ev(A, ctid, s_tr, 16);
       cons_sync();
-      for (int idx = ctid; idx < beam * HEAD_DIM; idx += MG_CONS) {
-        const int k = idx / HEAD_DIM, e = idx - k * HEAD_DIM;
+      // every load of the merge is issued before the first use: one L2 round trip for the whole fix-up
+      for (int idx = ctid; idx < beam * (HEAD_DIM / 2); idx += MG_CONS) {
+        const int k = idx / (HEAD_DIM / 2), e = (idx - k * (HEAD_DIM / 2)) * 2;
         const float* pb = cross_part + (static_cast<long long>(uh) * cg.S) * (MAX_BEAM * 68) + k * 68;
-        float mm = -INFINITY;
-        for (int s2 = 0; s2 < cg.S; ++s2) mm = fmaxf(mm, ldcg_f(pb + s2 * (MAX_BEAM * 68) + 64));
-        float a = 0.f, ll = 0.f;
-        for (int s2 = 0; s2 < cg.S; ++s2) {
-          const float ms = ldcg_f(pb + s2 * (MAX_BEAM * 68) + 64);
-          const float w = (ms == -INFINITY) ? 0.f : __expf(ms - mm);
-          a = fmaf(w, ldcg_f(pb + s2 * (MAX_BEAM * 68) + e), a);
-          ll = fmaf(w, ldcg_f(pb + s2 * (MAX_BEAM * 68) + 65), ll);
+        float2 ml[16], pv[16];
+#pragma unroll
+        for (int s2 = 0; s2 < 16; ++s2) {
+          ml[s2] = make_float2(-INFINITY, 0.f);
+          pv[s2] = make_float2(0.f, 0.f);
+          if (s2 < cg.S) {
+            ml[s2] = ldcg_f2(pb + s2 * (MAX_BEAM * 68) + 64);
+            pv[s2] = ldcg_f2(pb + s2 * (MAX_BEAM * 68) + e);
+          }
         }
-        ctx[static_cast<long long>(u * beam + k) * d + h * HEAD_DIM + e] = a / ll;
+        float mm = -INFINITY;
+#pragma unroll
+        for (int s2 = 0; s2 < 16; ++s2) mm = fmaxf(mm, ml[s2].x);
+        float ax = 0.f, ay = 0.f, ll = 0.f;
+#pragma unroll
+        for (int s2 = 0; s2 < 16; ++s2) {
+          const float w = (ml[s2].x == -INFINITY) ? 0.f : __expf(ml[s2].x - mm);
+          ax = fmaf(w, pv[s2].x, ax);
+          ay = fmaf(w, pv[s2].y, ay);
+          ll = fmaf(w, ml[s2].y, ll);
+        }
+        const float inv = 1.f / ll;
+        *reinterpret_cast<float2*>(ctx + static_cast<long long>(u * beam + k) * d + h * HEAD_DIM + e) = make_float2(ax * inv, ay * inv);
       }
     }
+    trace_ev(A, ctid, s_tr, 17);
     cons_sync();
   }
   rg.unit = unit;
@@ -711,7 +753,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs 
   {
     int lo, hi;
     cta_cols(A.d, lo, hi);
-    float* s_xown = s_stat + 768;
+    float* s_xown = s_stat + 784;
     for (int idx = ctid; idx < A.R * (hi - lo); idx += MG_CONS) {
       const int r = idx / (hi - lo), c = idx - r * (hi - lo);
       const float v = __half2float(A.tok_emb[static_cast<long long>(row_token(A, r)) * A.d + lo + c]) +
