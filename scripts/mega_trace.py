@@ -20,7 +20,7 @@ for i in range(3):
 print(h.timing())
 tt = h.debug_read_trace(2048).astype(np.int64)
 ev = tt[1024:1024+2*120].reshape(-1,2)
-print('events (id, t ns, dt):', [(int(a), int(b - ev[0,1]), int(b - ev[max(i-1,0),1])) for i, (a, b) in enumerate(ev[:120])])
+print('events (id, t ns, dt):', [(int(a), int(b - ev[0,1]), int(b - ev[max(i-1,0),1])) for i, (a, b) in enumerate(ev[:70])])
 t = tt[:2*262]
 # t[2k] = time barrier k was released (k=0: kernel start), t[2k+1] = time CTA 0 arrived at barrier k+1... (index k -> barrier k+1)
 rel = t[0::2]; arr = t[1::2]

@@ -32,11 +32,15 @@ constexpr int MG_CONS = MG_CONS_WARPS * 32;             // 320 consumer threads
 constexpr int MG_THREADS = MG_CONS + 32;                // + producer warp (lane 0 only)
 constexpr int MG_KC_MAX = 1536;
 constexpr int MG_STAGE_BYTES = 12 * MG_KC_MAX * 2;      // 36864: up to 12 weight-row chunks (or 288 keys of K / V)
-constexpr int MG_NSTAGE = 5;
+constexpr int MG_NSTAGE = 2;
 constexpr int MG_CA_KEYS_MAX = MG_STAGE_BYTES / 128;    // 288 keys per K (or V) chunk
-constexpr int MG_SCRATCH = 28672;                       // self-attention probabilities / cross-attention merge
+constexpr int MG_SCRATCH = 29696;                       // self-attention V rows + probabilities / cross-attention merge
+constexpr int MG_SLOT_BYTES = MG_CONS_WARPS * 448 * 2;  // per-warp cache-slot table of the warp's self-attention task
+constexpr int MG_LY_BYTES = 2 * 512;                    // double-buffered copy of the layer descriptor
 constexpr int MG_RED_FLOATS = (2 * 2 + 1) * MG_CONS_WARPS * 32;  // 2 buffers x 2 sets + LN partials
-constexpr int MG_SMEM = MG_NSTAGE * MG_STAGE_BYTES + 1024 + MG_RED_FLOATS * 4 + 4224 + MG_SCRATCH;
+constexpr int MG_SMEM = MG_NSTAGE * MG_STAGE_BYTES + 1024 + MG_RED_FLOATS * 4 + 4224 + MG_SCRATCH + MG_SLOT_BYTES + MG_LY_BYTES;
+static_assert(MG_SMEM <= 232448, "decoder pass: shared memory");
+static_assert(sizeof(MegaLayer) % 16 == 0 && sizeof(MegaLayer) <= 512, "layer descriptor is copied with 16-byte cp.async");
 // columns a thread accumulates per unit: the transposing reduction handles GP * NR <= 32 values
 __host__ __device__ constexpr int mg_gp(int nr) { return 32 / nr < 6 ? 32 / nr : 6; }
 // accumulator sets per thread: 2 x 6 columns for <= 5 rows (the stage holds 12 weight-row chunks), 1 x 4 for 8 rows
@@ -44,6 +48,18 @@ __host__ __device__ constexpr int mg_nset(int nr) { return nr <= 5 ? 2 : 1; }
 
 __device__ __forceinline__ float ldcg_f(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ float4 ldcg_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ float2 ldcg_f2(const float* p) { return __ldcg(reinterpret_cast<const float2*>(p)); }
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -112,6 +128,7 @@ __device__ __noinline__ void produce_gemv(Ring& rg, const MegaGemv& g, int gp) {
   k_split(g.K, n_chunks, kc);
   part_geom(kc, wpp, n_parts);
   const int G = gp * n_parts;
+  const uint64_t pol = l2_policy_evict_first();  // weights are read once per pass: do not let them flush the L2
   for (int g0 = lo; g0 < hi; g0 += G) {
     const int nc = min(G, hi - g0);
     for (int ch = 0; ch < n_chunks; ++ch) {
@@ -121,8 +138,8 @@ __device__ __noinline__ void produce_gemv(Ring& rg, const MegaGemv& g, int gp) {
       // chunk-major [chunk][N][kc] by the engine at load time).  Many small copies (one per 2.5 KB row) were bound by
       // the per-request rate of the copy engine (~0.6 us each, 590 GB/s aggregate).
       mbar_arrive_expect_tx(rg.full(st), static_cast<uint32_t>(nc * kc * 2));
-      bulk_load_1d(rg.data0 + st * MG_STAGE_BYTES, g.w + (static_cast<long long>(ch) * g.N + g0) * kc,
-                   static_cast<uint32_t>(nc * kc * 2), rg.full(st));
+      bulk_load_1d_hint(rg.data0 + st * MG_STAGE_BYTES, g.w + (static_cast<long long>(ch) * g.N + g0) * kc,
+                        static_cast<uint32_t>(nc * kc * 2), rg.full(st), pol);
       ++rg.unit;
     }
   }
@@ -148,6 +165,7 @@ __device__ __forceinline__ CrossGeom cross_geom(int n_utt, int H) {
 
 __device__ __noinline__ void produce_cross(Ring& rg, const MegaArgs& A, const MegaLayer& ly) {
   const CrossGeom cg = cross_geom(A.n_utt, A.H);
+  const uint64_t pol = l2_policy_evict_first();
   for (int task = blockIdx.x; task < cg.n_tasks; task += gridDim.x) {
     const int split = task % cg.S, uh = task / cg.S;
     const int t0 = split * cg.KS;
@@ -157,8 +175,8 @@ __device__ __noinline__ void produce_cross(Ring& rg, const MegaArgs& A, const Me
       const int st = rg.unit % MG_NSTAGE;
       mbar_wait(rg.empty(st), ((rg.unit / MG_NSTAGE) & 1u) ^ 1u);
       mbar_arrive_expect_tx(rg.full(st), static_cast<uint32_t>(nk * HEAD_DIM * 2));
-      bulk_load_1d(rg.data0 + st * MG_STAGE_BYTES, (kv == 0 ? ly.ck : ly.cv) + off, static_cast<uint32_t>(nk * HEAD_DIM * 2),
-                   rg.full(st));
+      bulk_load_1d_hint(rg.data0 + st * MG_STAGE_BYTES, (kv == 0 ? ly.ck : ly.cv) + off,
+                        static_cast<uint32_t>(nk * HEAD_DIM * 2), rg.full(st), pol);
       ++rg.unit;
     }
   }
@@ -425,70 +443,90 @@ __device__ __noinline__ void consume_gemv(Ring& rg, const MegaArgs& A, const Meg
 }
 
 // ------------------------------------------------------------------ consumer: self-attention phase
-// task = (row, head); one warp does the work (sequence lengths are <= 448 and typically < 30)
-__device__ __noinline__ void consume_self_attn(const MegaArgs& A, const MegaLayer& ly, int ctid, float* s_p, unsigned short* s_slot) {
+// task = (row, head), one warp each.  Lane t owns key t of a 32-key block: its K row and V row are requested together (one
+// L2 round trip for the whole block), the V rows are parked in shared memory (16-byte chunks XOR-swizzled by key) and the
+// P.V product then runs from shared memory with lanes over the head dimension.  The step position, the ping-pong flag and
+// the warp's cache-slot table are pass constants, read once at kernel start (`pos_dec`, `flipv`, `s_slot_tab`).
+__device__ __noinline__ void consume_self_attn(const MegaArgs& A, const MegaLayer& ly, int ctid, uint8_t* s_scr,
+                                               const unsigned short* s_slot_tab, int pos_dec, int flipv) {
   const int lane = ctid & 31, warp = ctid >> 5;
   const int d = A.d, H = A.H;
   const int n_tasks = A.R * H;
+  const bool pf = A.pf_len > 0;
+  const uint32_t sv = smem_u32(s_scr) + warp * 4224;
+  float* sp = reinterpret_cast<float*>(s_scr + warp * 4224 + 4096);
+  const unsigned short* my_slots = s_slot_tab + warp * 448;
+  const __half* kcache = ly.kcache;
+  const __half* vcache = ly.vcache;
+  int* s_tr = reinterpret_cast<int*>(s_scr) - 55;  // = s_stat + 1001 (trace cursor)
+  trace_ev(A, ctid, s_tr, 20);
   for (int base = blockIdx.x * MG_CONS_WARPS; base < n_tasks; base += gridDim.x * MG_CONS_WARPS) {
     const int task = base + warp;
     if (task < n_tasks) {
+      const bool tab = base == static_cast<int>(blockIdx.x) * MG_CONS_WARPS;
       const int r = task / H, h = task - r * H;
-      const int pos = row_pos(A, r);
+      const int pos = pf ? r % A.pf_len : pos_dec;
       const int own = row_slot(A, r);
-      const bool pf = A.pf_len > 0;
-      const int* indir = (*A.flip ? A.indir1 : A.indir0) + static_cast<long long>(r) * A.t_max;
+      const int* indir = (flipv ? A.indir1 : A.indir0) + static_cast<long long>(r) * A.t_max;
       const float* qr = A.q + static_cast<long long>(r) * d + h * HEAD_DIM;
-      float* sp = s_p + warp * 448;
-      unsigned short* ss = s_slot + warp * 448;
-      float qv[HEAD_DIM];
+      float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+      for (int t0 = 0; t0 <= pos; t0 += 32) {
+        const int t = t0 + lane;
+        const bool valid = t <= pos;
+        int slot = own;
+        if (valid && !pf && t != pos) slot = tab ? static_cast<int>(my_slots[t]) : __ldcg(indir + t);
+        uint4 ku[8], vu[8];
 #pragma unroll
-      for (int i = 0; i < HEAD_DIM / 4; ++i) {
-        const float4 v = ldcg_f4(qr + 4 * i);
-        qv[4 * i] = v.x; qv[4 * i + 1] = v.y; qv[4 * i + 2] = v.z; qv[4 * i + 3] = v.w;
-      }
-      float mx = -INFINITY;
-      for (int t = lane; t <= pos; t += 32) {
-        const int slot = (pf || t == pos) ? own : indir[t];
-        ss[t] = static_cast<unsigned short>(slot);
-        const uint4* kr = reinterpret_cast<const uint4*>(ly.kcache + (static_cast<long long>(slot) * A.t_max + t) * d + h * HEAD_DIM);
-        float s = 0.f;
+        for (int i = 0; i < 8; ++i) ku[i] = vu[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) {
+          const long long off = (static_cast<long long>(slot) * A.t_max + t) * d + h * HEAD_DIM;
+          const uint4* kr = reinterpret_cast<const uint4*>(kcache + off);
+          const uint4* vr = reinterpret_cast<const uint4*>(vcache + off);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ku[i] = __ldcg(kr + i);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vu[i] = __ldcg(vr + i);
+        }
+        float sc0 = 0.f, sc1 = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const uint4 u = __ldcg(kr + i);
-          const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(h2[j]);
-            s = fmaf(qv[8 * i + 2 * j], f.x, s);
-            s = fmaf(qv[8 * i + 2 * j + 1], f.y, s);
-          }
+          const float4 qa = ldcg_f4(qr + 8 * i), qb = ldcg_f4(qr + 8 * i + 4);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&ku[i]);
+          const float2 f0 = __half22float2(h2[0]), f1 = __half22float2(h2[1]), f2 = __half22float2(h2[2]), f3 = __half22float2(h2[3]);
+          sc0 = fmaf(qa.x, f0.x, sc0); sc1 = fmaf(qa.y, f0.y, sc1);
+          sc0 = fmaf(qa.z, f1.x, sc0); sc1 = fmaf(qa.w, f1.y, sc1);
+          sc0 = fmaf(qb.x, f2.x, sc0); sc1 = fmaf(qb.y, f2.y, sc1);
+          sc0 = fmaf(qb.z, f3.x, sc0); sc1 = fmaf(qb.w, f3.y, sc1);
         }
-        s *= 0.125f;
-        sp[t] = s;
-        mx = fmaxf(mx, s);
+        const float sc = valid ? (sc0 + sc1) * 0.125f : -INFINITY;
+        trace_ev(A, ctid, s_tr, 21);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sts128(sv + lane * 128 + ((i ^ (lane & 7)) << 4), vu[i]);
+        const float mn = fmaxf(m, warp_max(sc));
+        const float resc = __expf(m - mn);
+        const float p = valid ? __expf(sc - mn) : 0.f;
+        l = fmaf(l, resc, warp_sum(p));
+        o0 *= resc;
+        o1 *= resc;
+        m = mn;
+        sp[lane] = p;
+        __syncwarp();
+        trace_ev(A, ctid, s_tr, 22);
+        const int nb = min(32, pos - t0 + 1);
+#pragma unroll 4
+        for (int tt = 0; tt < nb; ++tt) {
+          const float pp = sp[tt];
+          const uint32_t u = lds32(sv + tt * 128 + (((lane >> 2) ^ (tt & 7)) << 4) + ((lane & 3) << 2));
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u));
+          o0 = fmaf(pp, f.x, o0);
+          o1 = fmaf(pp, f.y, o1);
+        }
+        __syncwarp();
       }
-      mx = warp_max(mx);
-      float sum = 0.f;
-      for (int t = lane; t <= pos; t += 32) {
-        const float p = __expf(sp[t] - mx);
-        sp[t] = p;
-        sum += p;
-      }
-      sum = warp_sum(sum);
-      __syncwarp();
-      float o0 = 0.f, o1 = 0.f;
-      for (int t = 0; t <= pos; ++t) {
-        const float p = sp[t];
-        const unsigned vv = __ldcg(reinterpret_cast<const unsigned*>(ly.vcache + (static_cast<long long>(ss[t]) * A.t_max + t) * d +
-                                                                   h * HEAD_DIM + 2 * lane));
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&vv));
-        o0 = fmaf(p, f.x, o0);
-        o1 = fmaf(p, f.y, o1);
-      }
-      const float inv = 1.0f / sum;
+      trace_ev(A, ctid, s_tr, 23);
+      const float inv = 1.0f / l;
       *reinterpret_cast<float2*>(A.ctx + static_cast<long long>(r) * d + h * HEAD_DIM + 2 * lane) = make_float2(o0 * inv, o1 * inv);
-      __syncwarp();
+      trace_ev(A, ctid, s_tr, 24);
     }
   }
 }
@@ -708,7 +746,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs 
   uint64_t* bars = reinterpret_cast<uint64_t*>(mg_smem + MG_NSTAGE * MG_STAGE_BYTES);
   float* s_red = reinterpret_cast<float*>(mg_smem + MG_NSTAGE * MG_STAGE_BYTES + 1024);
   float* s_stat = s_red + MG_RED_FLOATS;  // 1056 floats: [0,256) unused, bias, s2, own residual columns, flags
-  float* s_part = s_stat + 1056;  // [40][NB][66] for the cross-attention merge; also self-attention scratch
+  float* s_part = s_stat + 1056;  // [warps][NB][66] for the cross-attention merge; also self-attention scratch
+  unsigned short* s_slot_tab = reinterpret_cast<unsigned short*>(reinterpret_cast<uint8_t*>(s_part) + MG_SCRATCH);
+  MegaLayer* s_ly = reinterpret_cast<MegaLayer*>(reinterpret_cast<uint8_t*>(s_slot_tab) + MG_SLOT_BYTES);  // [2] at 512 B
   Ring rg;
   rg.data = ring_data;
   rg.data0 = smem_u32(ring_data);
@@ -749,6 +789,24 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs 
   const unsigned epoch0 = epoch;
   if (ctid == 0) *reinterpret_cast<int*>(s_stat + 1001) = 0;
   if (A.trace != nullptr && blockIdx.x == 0 && ctid == 0) A.trace[0] = globaltimer_ns();
+  // layer descriptors travel to shared memory one layer ahead (cp.async), so no phase starts with a global round trip
+  auto prefetch_layer = [&](int l) {
+    if (ctid < static_cast<int>(sizeof(MegaLayer) / 16))
+      cp_async16(smem_u32(reinterpret_cast<uint8_t*>(s_ly) + (l & 1) * 512) + ctid * 16,
+                 reinterpret_cast<const uint8_t*>(A.layers + l) + ctid * 16);
+  };
+  if (L > 0) prefetch_layer(0);
+  // pass constants: step position, indirection ping-pong flag, and the cache slots of this warp's self-attention task
+  const int pos_dec = A.pf_len > 0 ? 0 : A.st->pos;
+  const int flipv = *A.flip;
+  if (A.pf_len == 0) {
+    const int task = blockIdx.x * MG_CONS_WARPS + (ctid >> 5);
+    if (task < A.R * A.H) {
+      const int* indir = (flipv ? A.indir1 : A.indir0) + static_cast<long long>(task / A.H) * A.t_max;
+      for (int t = ctid & 31; t < pos_dec; t += 32) s_slot_tab[(ctid >> 5) * 448 + t] = static_cast<unsigned short>(indir[t]);
+    }
+  }
+  cp_async_wait_all();
   // phase 0: token + positional embedding; every CTA produces (and keeps) the residual-stream columns it owns
   {
     int lo, hi;
@@ -764,10 +822,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs 
   }
   grid_barrier(A, epoch, ctid, epoch0);
   for (int l = 0; l < L; ++l) {
-    const MegaLayer& ly = A.layers[l];
+    const MegaLayer& ly = *reinterpret_cast<const MegaLayer*>(reinterpret_cast<const uint8_t*>(s_ly) + (l & 1) * 512);
+    if (l + 1 < L) prefetch_layer(l + 1);  // the other buffer was last read in layer l - 1
     consume_gemv<NR>(rg, A, ly.qkv, &ly, ctid, s_red, s_stat);
     grid_barrier(A, epoch, ctid, epoch0);
-    consume_self_attn(A, ly, ctid, s_part, reinterpret_cast<unsigned short*>(s_part + MG_CONS_WARPS * 448));
+    consume_self_attn(A, ly, ctid, reinterpret_cast<uint8_t*>(s_part), s_slot_tab, pos_dec, flipv);
     grid_barrier(A, epoch, ctid, epoch0);
     consume_gemv<NR>(rg, A, ly.o, &ly, ctid, s_red, s_stat);
     grid_barrier(A, epoch, ctid, epoch0);
@@ -780,6 +839,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs 
     consume_gemv<NR>(rg, A, ly.fc1, &ly, ctid, s_red, s_stat);
     grid_barrier(A, epoch, ctid, epoch0);
     consume_gemv<NR>(rg, A, ly.fc2, &ly, ctid, s_red, s_stat);
+    cp_async_wait_all();  // next layer's descriptor has landed; the barrier's CTA sync publishes it
     grid_barrier(A, epoch, ctid, epoch0);
   }
   if (A.with_logits) consume_gemv<NR>(rg, A, A.vocab, nullptr, ctid, s_red, s_stat);
@@ -845,7 +905,10 @@ void dec_pass_run(const MegaArgs& a, int num_sms, cudaStream_t stream) {
   WISB_REQUIRE(a.d % 64 == 0 && a.d <= MG_KC_MAX, "decoder pass: d_model <= 1536");
   WISB_REQUIRE((a.d + num_sms - 1) / num_sms <= 16, "decoder pass: too few SMs for the per-CTA residual slice");
   WISB_REQUIRE(num_sms <= 160, "decoder pass: more SMs than barrier flags");
-  static bool attr_set = false;
+  static bool attr_done[64] = {};  // per device: function attributes belong to the device's context
+  int dev = 0;
+  WISB_CUDA(cudaGetDevice(&dev));
+  bool& attr_set = attr_done[dev & 63];
   if (!attr_set) {
     WISB_CUDA(cudaFuncSetAttribute(dec_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
     WISB_CUDA(cudaFuncSetAttribute(dec_pass_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));

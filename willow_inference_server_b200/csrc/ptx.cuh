@@ -100,6 +100,19 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
                : "memory");
 }
 
+// L2 eviction policy for data that is read exactly once per pass (weight streams): first in line for eviction, so the
+// small re-read working set (activations, self-attention cache) stays resident in the 126 MB L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_load_1d_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar), "l"(pol)
+               : "memory");
+}
+
 // ----------------------------------------------------------------------------- tcgen05 / TMEM
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
