@@ -7,8 +7,9 @@
 // roofline even with PDL).  Here
 //   * one CTA per SM, every CTA owns a fixed column slice of every weight matrix;
 //   * a dedicated producer thread per CTA walks the (static) list of weight chunks of ALL phases and streams them into a
-//     5-stage shared-memory ring with cp.async.bulk (TMA) + mbarrier complete_tx -- it never waits for activations, so
-//     the HBM stream keeps running across phase boundaries (the ring holds several phases of look-ahead);
+//     2-stage shared-memory ring with cp.async.bulk (TMA, L2 evict-first) + mbarrier complete_tx -- it never waits for
+//     activations, so the HBM stream keeps running across phase boundaries.  (Two stages on purpose: with 5 stages the
+//     180 KB of bulk copies in flight per SM queued every demand load -- activation reloads, K/V rows -- behind them.)
 //   * consumer warps wait only on (a) the ring and (b) a flag-based grid barrier between phases (per-CTA epoch flags,
 //     no atomics), and read activations with L1-bypassing loads;
 //   * activations stay fp32; LayerNorm (single-pass sum / sum-of-squares statistics in fp32) is applied in registers while staging x.
