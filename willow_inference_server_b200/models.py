@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import os
 import threading
+import zlib
 from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
 
@@ -75,7 +76,7 @@ def _features_array(features) -> np.ndarray:
 class Whisper:
     def __init__(self, model_path, device: str = "cuda", *, device_index=0, compute_type: str = "default",
                  inter_threads: int = 1, intra_threads: int = 0, max_queued_batches: int = 0, files=None,
-                 _handles=None, **_ignored):
+                 reuse_encoder=None, _handles=None, **_ignored):
         if device != "cuda":
             raise ValueError("willow_inference_server_b200.models.Whisper runs on device='cuda' only (no CPU fallback)")
         idx = [device_index] if isinstance(device_index, int) else list(device_index)
@@ -88,12 +89,30 @@ class Whisper:
             self._handles = list(_handles)
         else:
             path = str(model_path)
-            if os.path.isdir(path):
+            if os.path.isdir(path) and os.path.isfile(os.path.join(path, "model.wisb")):
                 path = os.path.join(path, "model.wisb")
-            if not os.path.isfile(path):
-                raise RuntimeError(f"Unable to open weight blob '{path}' (expected a WISB200 blob)")
-            blob = np.fromfile(path, np.uint8)  # read once, copied to every replica
+            if os.path.isfile(path):
+                blob = np.fromfile(path, np.uint8)  # read once, copied to every replica
+            elif os.path.isdir(path) and any(os.path.exists(os.path.join(path, f)) for f in
+                                             ("model.bin", "model.safetensors", "model.safetensors.index.json",
+                                              "pytorch_model.bin")):
+                # a CTranslate2 directory as main.py:342 passes it, or an HF checkpoint: converted in memory
+                from . import loaders, weights as _W
+
+                dims, tensors = loaders.load_any(path)
+                blob = np.zeros(_W.blob_nbytes(tensors), np.uint8)
+                _W.write_blob_into(blob, dims, tensors)
+            else:
+                raise RuntimeError(f"Unable to open model '{path}' (expected model.wisb, a CTranslate2 model.bin "
+                                   "or a Hugging Face Whisper checkpoint)")
             self._handles = [_lib.Handle.from_host(blob, d) for d in idx]
+        # detect_language -> generate -> (translate) on the same window encode once; opt-in because a
+        # caller that replays identical features on purpose (a benchmark) must not have work skipped behind its back
+        if reuse_encoder is None:
+            reuse_encoder = os.environ.get("WISB_ENCODER_CACHE", "0") not in ("", "0")
+        self.reuse_encoder = bool(reuse_encoder)
+        for h in self._handles:
+            h.set_option("encoder_cache", 1 if self.reuse_encoder else 0)
         self._dims = self._handles[0].dims()
         self._pool = ThreadPoolExecutor(max_workers=len(self._handles)) if len(self._handles) > 1 else None
         self._rr = 0
@@ -112,8 +131,11 @@ class Whisper:
     def dims(self) -> dict:
         return dict(self._dims)
 
-    def _split(self, n: int):
+    def _split(self, n: int, mel=None):
         k = len(self._handles)
+        if k > 1 and self.reuse_encoder and n <= 2 and mel is not None:
+            # same features -> same replica, so the cached encoder output is found again
+            return [(zlib.crc32(np.ascontiguousarray(mel[0, :, :64]).tobytes()) % k, 0, n)]
         if k == 1 or n == 1:
             with self._lock:
                 i = self._rr % k
@@ -152,7 +174,7 @@ class Whisper:
             raise ValueError("timestamp decoding is not implemented: the prompt must contain <|notimestamps|>")
         extra = [int(t) for t in suppress_tokens if t >= 0]
         p = np.asarray(prompts, np.int32)
-        parts = self._split(n)
+        parts = self._split(n, mel)
 
         def job(i, s, e):
             return lambda: self._handles[i].generate(mel[s:e], p[s:e], beam_size, patience, length_penalty, max_length, extra)
@@ -166,7 +188,7 @@ class Whisper:
 
     def detect_language(self, features):
         mel = _features_array(features)
-        parts = self._split(mel.shape[0])
+        parts = self._split(mel.shape[0], mel)
 
         def job(i, s, e):
             return lambda: self._handles[i].detect_language(mel[s:e])
