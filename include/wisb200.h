@@ -88,6 +88,16 @@ int wisb_debug_encode(wisb_handle* h, const float* mel, int B, float* enc_out, i
 /* teacher-forced raw decoder logits (no processors) for utterance 0: float32 [n_tokens, n_vocab] */
 int wisb_debug_forced_logits(wisb_handle* h, const float* mel, const int32_t* tokens, int n_tokens, float* logits_out);
 
+/* ---- (6) FLAC ingest (host code, no handle, no GPU): replaces the decode half of `librosa.load(audio_file, sr=16000)`
+ * (/root/reference/main.py:579) for the FLAC files WIS is tested with (client/{3sec,10sec,30sec}.flac).
+ * wisb_flac_info: stream parameters, number of inter-channel frames and the PCM MD5 from STREAMINFO (any pointer may be NULL).
+ * wisb_flac_decode: interleaved int32 samples [n_frames, channels]; every frame's CRC-8 / CRC-16 is checked.
+ * Both return 0 or a non-zero code with the reason in wisb_flac_last_error() (thread-local). */
+const char* wisb_flac_last_error(void);
+int wisb_flac_info(const void* data, size_t nbytes, int32_t* sample_rate, int32_t* channels, int32_t* bits_per_sample,
+                   int64_t* n_frames, uint8_t* md5_16);
+int wisb_flac_decode(const void* data, size_t nbytes, int32_t* out_interleaved, int64_t capacity_frames, int64_t* n_frames);
+
 #ifdef __cplusplus
 }
 #endif

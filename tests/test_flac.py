@@ -1,0 +1,111 @@
+"""FLAC ingest: csrc/flac.cu through the C ABI and audio.decode_flac -- host code, runs without a GPU.
+
+Goldens: the PCM MD5s of the reference's fixtures client/{3sec,10sec,30sec}.flac (parsed from
+their STREAMINFO) when /root/reference is present, plus streams made by tests/flac_writer.py for every decoder path
+the libFLAC-made mono fixtures do not reach."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from tests import flac_writer as fw
+from willow_inference_server_b200 import _lib, audio
+
+REF = "/root/reference/client"
+FIXTURES = [("3sec.flac", 61440, "ad790df21d4d9d223d3f34227b5cfedd"),
+            ("10sec.flac", 171008, "c5b99673d012d9a8f5d19dd68874a121"),
+            ("30sec.flac", 467968, "3a541ad6463fe6e884e5995212b518fa")]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference fixtures are only present in the build container")
+@pytest.mark.parametrize("name,n,md5", FIXTURES)
+def test_reference_fixtures_decode_to_their_md5(name, n, md5):
+    pcm, sr = audio.decode_flac(os.path.join(REF, name))          # verify=True already checks STREAMINFO's MD5
+    assert sr == 16000 and pcm.dtype == np.int16 and pcm.shape == (n,)
+    assert hashlib.md5(pcm.astype("<i2").tobytes()).hexdigest() == md5
+    x = audio.load_audio(os.path.join(REF, name))
+    assert x.dtype == np.float32 and x.shape == (n,) and np.abs(x).max() <= 1.0
+    assert np.array_equal(x, pcm.astype(np.float32) / 32768.0)
+
+
+def _signal(n, ch, bps, seed):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n)
+    amp = (1 << (bps - 1)) * 0.4
+    x = np.stack([amp * np.sin(2 * np.pi * (0.01 + 0.003 * c) * t + c) + rng.normal(0, amp * 0.02, n) for c in range(ch)], 1)
+    return np.clip(np.round(x), -(1 << (bps - 1)), (1 << (bps - 1)) - 1).astype(np.int64)
+
+
+def _roundtrip(pcm, **kw):
+    data = fw.encode(pcm, **kw)
+    got, sr = audio.decode_flac(data)
+    want = np.asarray(pcm)
+    want = want[:, 0] if want.ndim == 2 and want.shape[1] == 1 else want
+    assert got.shape == want.shape and np.array_equal(got.astype(np.int64), want), kw
+    return data
+
+
+def test_every_subframe_type_and_residual_coding():
+    n = 4096 + 1000 + 192 + 37
+    x = _signal(n, 1, 16, 1)[:, 0]
+    x[4096 : 4096 + 1000] = -1234                       # constant block
+    blocks = [4096, 1000, 192, 37]
+    for method in (0, 1):
+        specs = [[{"kind": "lpc", "order": 3, "coefs": [1400, -900, 200], "shift": 9, "prec": 12, "method": method, "po": 3,
+                   "escape": (2,)}],
+                 [{"kind": "constant"}],
+                 [{"kind": "fixed", "order": 4, "method": method, "po": 2, "escape": (0,)}],
+                 [{"kind": "verbatim"}]]
+        _roundtrip(x, blocks=blocks, specs=specs)
+    for order in range(5):
+        _roundtrip(x[:2048], blocks=[2048], specs=[[{"kind": "fixed", "order": order, "po": 4}]])
+    # 32nd-order LPC with a long warm-up and the largest legal coefficient precision
+    coefs = [((-1) ** j) * (3000 >> (j // 4)) for j in range(32)]
+    _roundtrip(x[:1024], blocks=[1024], specs=[[{"kind": "lpc", "order": 32, "coefs": coefs, "shift": 14, "prec": 15, "po": 0}]])
+
+
+@pytest.mark.parametrize("bps", [8, 16, 24])
+def test_stereo_decorrelation_wasted_bits_and_sample_widths(bps):
+    n = 3 * 1152 + 500
+    x = _signal(n, 2, bps, 7)
+    x[1152:2304] = (x[1152:2304] >> 3) << 3             # three wasted bits in the second block
+    blocks = [1152, 1152, 1152, 500]
+    modes = ["ls", "sr", "ms", "indep"]
+    specs = [[{"kind": "fixed", "order": 2, "po": 1}, {"kind": "fixed", "order": 1, "po": 0}],
+             [{"kind": "fixed", "order": 2, "po": 0, "wasted": 3}, {"kind": "fixed", "order": 0, "po": 2, "wasted": 3}],
+             [{"kind": "lpc", "order": 2, "coefs": [500, -200], "shift": 8, "prec": 11, "po": 2}, {"kind": "fixed", "order": 3, "po": 0}],
+             [{"kind": "verbatim"}, {"kind": "fixed", "order": 1, "po": 2}]]
+    data = _roundtrip(x, bps=bps, blocks=blocks, stereo_modes=modes, specs=specs)
+    pcm, sr, got_bps, md5 = _lib.flac_decode(data)
+    assert (sr, got_bps, pcm.shape) == (16000, bps, (n, 2)) and any(md5)
+    if bps <= 16:
+        assert audio.load_audio(data).shape == (n,)     # stereo is averaged to mono, as librosa.load(mono=True) does
+
+
+def test_many_frames_unknown_md5_and_8_channels():
+    x = _signal(300 * 256 + 13, 1, 16, 3)[:, 0]
+    _roundtrip(x, blocks=[256] * 300 + [13], md5=False)  # frame numbers >= 128 need the multi-byte number coding
+    y = _signal(1024, 8, 16, 4)
+    _roundtrip(y, blocks=[1024])
+
+
+def test_corruption_is_detected():
+    x = _signal(4096, 1, 16, 5)[:, 0]
+    good = fw.encode(x, blocks=[4096])
+    for where in (len(good) // 2, len(good) - 1):        # payload byte, CRC-16 byte
+        bad = bytearray(good)
+        bad[where] ^= 0x10
+        with pytest.raises(ValueError, match="FLAC"):
+            audio.decode_flac(bytes(bad))
+    with pytest.raises(ValueError, match="fLaC"):
+        audio.decode_flac(b"RIFF" + good[4:])
+    with pytest.raises(ValueError, match="FLAC"):
+        audio.decode_flac(good[: len(good) // 2])        # truncated
+    lying = bytearray(good)
+    lying[26 + 8] ^= 0xFF                                 # MD5 field of STREAMINFO (4 + 4 + 18 = offset 26)
+    with pytest.raises(ValueError, match="MD5"):
+        audio.decode_flac(bytes(lying))
+    assert audio.decode_flac(bytes(lying), verify=False)[0].shape == (4096,)
+    with pytest.raises(ValueError, match="resampling"):
+        audio.load_audio(fw.encode(x, blocks=[4096], sample_rate=44100))

@@ -39,6 +39,9 @@ _SIGS = {
     "wisb_debug_read_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "wisb_debug_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "wisb_debug_forced_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "wisb_flac_last_error": (C.c_char_p, []),
+    "wisb_flac_info": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wisb_flac_decode": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 EXPORTS = sorted(_SIGS)
 
@@ -212,3 +215,18 @@ class Handle:
         out = np.zeros((tokens.shape[0], self.dims()["n_vocab"]), np.float32)
         check(lib().wisb_debug_forced_logits(self._h, ptr(mel), ptr(tokens), tokens.shape[0], ptr(out)))
         return out
+
+
+def flac_decode(data: bytes):
+    """FLAC stream -> (int32 ndarray [n_frames, channels], sample_rate, bits_per_sample, md5 bytes).  Host code only."""
+    l = lib()
+    buf = np.frombuffer(data, np.uint8)
+    sr, ch, bps, n = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+    md5 = (C.c_uint8 * 16)()
+    if l.wisb_flac_info(buf.ctypes.data, buf.size, C.byref(sr), C.byref(ch), C.byref(bps), C.byref(n), md5):
+        raise ValueError("FLAC: " + l.wisb_flac_last_error().decode())
+    out = np.zeros((n.value, ch.value), np.int32)
+    got = C.c_int64()
+    if l.wisb_flac_decode(buf.ctypes.data, buf.size, out.ctypes.data, n.value, C.byref(got)):
+        raise ValueError("FLAC: " + l.wisb_flac_last_error().decode())
+    return out[: got.value], sr.value, bps.value, bytes(md5)
