@@ -82,3 +82,18 @@ def test_bad_arguments():
         h.logmel(np.zeros(10, np.float64), [0], [10])
     with pytest.raises(ValueError):
         audio.log_mel_spectrogram(np.zeros((2, 100), np.float32))
+
+
+def test_long_audio_windows_are_framed_on_the_gpu():
+    # chunk_iter windows come straight out of one PCM buffer (offset + length), padding fused --
+    # identical to the reference recipe log_mel_spectrogram(pad_or_trim(chunk)) window by window
+    from willow_inference_server_b200 import audio
+
+    rng = np.random.default_rng(5)
+    x = (0.3 * np.sin(np.arange(75 * 16000) * 0.05) + 0.05 * rng.standard_normal(75 * 16000)).astype(np.float32)
+    mel, strides = audio.log_mel_chunks(x)
+    want = [(audio.log_mel_spectrogram(audio.pad_or_trim(c)).numpy(), s) for c, s in audio.chunk_iter(x)]
+    assert mel.shape == (len(want), 80, 3000) and strides == [s for _, s in want] and len(want) == 6
+    for i, (w, _) in enumerate(want):
+        assert np.array_equal(mel[i], w), i
+    assert audio.log_mel_chunks(np.zeros(0, np.float32))[0].shape == (0, 80, 3000)

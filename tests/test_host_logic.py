@@ -91,3 +91,45 @@ def test_no_gpu_fails_loudly():
         _lib.Handle.frontend(0)
     with pytest.raises(RuntimeError):
         audio.log_mel_spectrogram(np.zeros(16000, np.float32))
+
+
+def test_chunk_table_is_chunk_iter_as_index_arithmetic(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "host_logic.json")))
+    totals = [int(n) for n in g["chunk_iter"]] + [1, 63999, 64001, 352000, 352001, 576000, 224000 * 3 + 5]
+    for total in totals:
+        x = np.arange(total, dtype=np.float32)
+        want = [(int(c[0]), c.shape[0], s) for c, s in audio.chunk_iter(x)]
+        offs, lens, strides = audio.chunk_table(total)
+        assert [(int(o), int(n), st) for o, n, st in zip(offs, lens, strides)] == want, total
+
+
+def test_transcribe_long_orchestration(monkeypatch):
+    # windows -> one batched generate -> LCS merge, with a fake front end and a fake engine (host logic only)
+    from willow_inference_server_b200.models import WhisperGenerationResult
+
+    class Tok:
+        all_special_ids = [50257, 50258]
+
+    windows = [[1, 2, 3, 4, 5, 6, 50257], [4, 5, 6, 7, 8, 9], [8, 9, 10, 11]]
+    calls = []
+
+    class Engine:
+        def generate(self, features, prompts, **kw):
+            calls.append((features.array.shape[0], prompts, kw))
+            start = int(features.array[0, 0, 0])
+            return [WhisperGenerationResult([windows[start + i]]) for i in range(features.array.shape[0])]
+
+    def fake_chunks(audio_, handle=None):
+        mel = np.zeros((3, 80, 3000), np.float32)
+        mel[:, 0, 0] = np.arange(3)
+        return mel, [(352000, 0, 64000), (352000, 64000, 64000), (100000, 64000, 0)]
+
+    monkeypatch.setattr(audio, "log_mel_chunks", fake_chunks)
+    out = audio.transcribe_long(Engine(), np.zeros(800000, np.float32), [50258, 50259, 50359, 50363], Tok(), beam_size=3)
+    assert out.tolist() == list(range(1, 12))                     # the SURVEY 8c(iii) stitching example
+    assert len(calls) == 1 and calls[0][0] == 3 and calls[0][2] == {"beam_size": 3}
+    calls.clear()
+    out = audio.transcribe_long(Engine(), np.zeros(800000, np.float32), [50258], Tok(), max_windows_per_call=2)
+    assert out.tolist() == list(range(1, 12)) and [c[0] for c in calls] == [2, 1]
+    monkeypatch.setattr(audio, "log_mel_chunks", lambda a, handle=None: (fake_chunks(a)[0][:1], fake_chunks(a)[1][:1]))
+    assert audio.transcribe_long(Engine(), np.zeros(10, np.float32), [50258], Tok()).tolist() == [1, 2, 3, 4, 5, 6]

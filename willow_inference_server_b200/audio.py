@@ -116,6 +116,65 @@ def chunk_iter(inputs):
             yield piece, (piece.shape[0], left, right)
 
 
+def chunk_table(total: int):
+    """The windows ``chunk_iter`` yields for a ``total``-sample input, as index arithmetic only:
+    (offsets int64 [N], lengths int32 [N], strides [(length, left, right)] * N)."""
+    step = chunk_len - stride_left - stride_right
+    offs, lens, strides = [], [], []
+    for start in range(0, total, step):
+        n = min(chunk_len, total - start)
+        left = 0 if start == 0 else stride_left
+        right = 0 if start + step + stride_left >= total else stride_right
+        if n > left:
+            offs.append(start)
+            lens.append(n)
+            strides.append((n, left, right))
+    return np.asarray(offs, np.int64), np.asarray(lens, np.int32), strides
+
+
+def log_mel_chunks(audio, handle=None):
+    """Long-audio front end (main.py:603-611 does ``[log_mel_spectrogram(pad_or_trim(c)) for c in chunk_iter(audio)]``):
+    every 22-s window is framed by the log-mel kernel straight out of the one PCM buffer (offset + length per window,
+    zero padding to 30 s fused), so neither the padded copies nor a [N, 480000] batch is ever materialised.
+    Returns (float32 [N, 80, 3000], strides) with the strides ``chunk_iter`` would have produced."""
+    pcm = np.asarray(audio)
+    if pcm.dtype not in (np.float32, np.int16):
+        pcm = pcm.astype(np.float32)
+    if pcm.ndim != 1:
+        raise ValueError("audio must be a 1-D array of 16 kHz samples")
+    offs, lens, strides = chunk_table(pcm.shape[0])
+    if not strides:
+        return np.zeros((0, N_MELS, N_FRAMES), np.float32), strides
+    return (handle or _get_frontend()).logmel(np.ascontiguousarray(pcm), offs, lens), strides
+
+
+def transcribe_long(model, audio, prompt, tokenizer, *, beam_size: int = 5, batcher=None, max_windows_per_call: int = 64,
+                    **generate_options):
+    """The long-audio path of ``do_whisper`` (main.py:582-617, 676-714) on top of the pieces above: window the
+    utterance, decode all windows as batch rows (the reference goes two at a time, ``concurrent_gpu_chunks``), stitch
+    the token lists with ``find_longest_common_sequence``.  ``model`` is a ``models.Whisper`` (or anything with its
+    ``generate``); with ``batcher`` (a ``TranscribeBatcher``) the windows join other requests' batches.
+    Returns the merged token ids (numpy int array), ready for ``whisper_processor.decode``."""
+    from .models import StorageView
+
+    mel, strides = log_mel_chunks(audio)
+    if not strides:
+        return np.zeros(0, np.int64)
+    seqs = []
+    for s in range(0, mel.shape[0], max_windows_per_call):
+        part = mel[s : s + max_windows_per_call]
+        if batcher is not None:
+            res = batcher.submit(part, prompt, beam_size=beam_size, **generate_options).result()
+        else:
+            res = model.generate(StorageView.from_array(part), [list(prompt)] * part.shape[0], beam_size=beam_size,
+                                 **generate_options)
+        seqs += [r.sequences_ids[0] for r in res]
+    if len(seqs) == 1:
+        special = set(tokenizer.all_special_ids)
+        return np.array([t for t in seqs[0] if t not in special])
+    return find_longest_common_sequence([(ids, st) for ids, st in zip(seqs, strides)], tokenizer)
+
+
 def find_longest_common_sequence(sequences, tokenizer):
     """Token-level stitch of overlapping windows -- wis/audio.py:139-159 (same scoring: fraction of matches + i/10000,
     at least two matches).  Unlike the reference this does not raise when a later window is longer than the text
