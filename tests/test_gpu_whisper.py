@@ -228,3 +228,37 @@ def test_batcher_over_the_real_engine(pair):
         got = [f.result(timeout=60)[0].sequences_ids[0] for f in futs]
     assert got == want                       # batch-position invariance makes the coalesced call equal to the direct one
     assert b.stats["engine_calls"] < 4
+
+
+def test_two_replicas_in_one_process():
+    # the reference's multi-GPU mode: ONE process, ctranslate2-style device_index=[0..N-1] replicas (main.py:295,346);
+    # every kernel's function attributes must be configured on every device, not once per process
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    from willow_inference_server_b200 import _lib, weights as W
+
+    dims, oracle, h0 = model_pair()
+    tensors = W.synth_engine_tensors(dims, seed=11, eot_ramp=(10, 8.0))
+    buf = np.zeros(W.blob_nbytes(tensors), np.uint8)
+    W.write_blob_into(buf, dims, tensors)
+    h1 = _lib.Handle.from_host(buf, 1)
+    mel = mel_inputs(4)
+    one = models.Whisper(None, device="cuda", _handles=[h0])
+    want = [r.sequences_ids[0] for r in one.generate(models.StorageView.from_array(mel), [PROMPT] * 4, beam_size=5)]
+    two = models.Whisper(None, device="cuda", device_index=[0, 1], _handles=[h0, h1])
+    for _ in range(2):
+        got = [r.sequences_ids[0] for r in two.generate(models.StorageView.from_array(mel), [PROMPT] * 4, beam_size=5)]
+        assert got == want
+    # replica 1 alone, both decoder implementations, and the front end on the second device
+    for mega in (1, 0):
+        h1.set_option("decoder_mega", mega)
+        solo = models.Whisper(None, device="cuda", device_index=[1], _handles=[h1])
+        assert [r.sequences_ids[0] for r in solo.generate(models.StorageView.from_array(mel[:2]), [PROMPT] * 2, beam_size=5)] == want[:2]
+    h1.set_option("decoder_mega", 1)
+    langs = two.detect_language(models.StorageView.from_array(mel[:2]))
+    assert [t for t, _ in langs[0]][:3] == [t for t, _ in one.detect_language(models.StorageView.from_array(mel[:1]))[0]][:3]
+    pcm = np.zeros(16000, np.float32)
+    assert np.array_equal(h1.logmel(pcm, [0], [16000]), h0.logmel(pcm, [0], [16000]))
+    h1.close()

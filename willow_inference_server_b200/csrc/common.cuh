@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <stdexcept>
 #include <string>
 
@@ -35,6 +36,20 @@ struct Error : std::runtime_error {
   do {                                                \
     if (!(cond)) throw ::wisb::Error(1, std::string(msg)); \
   } while (0)
+
+// Function attributes (dynamic shared memory size ...) belong to a device's context: a process that drives several GPUs
+// (ctranslate2-style device_index=[0..N-1] replicas, /root/reference/main.py:295,346) must set them once PER DEVICE.
+// `done` is a per-call-site bit mask of devices already configured (a benign race sets an attribute twice).
+template <typename F>
+inline void once_per_device(std::atomic<unsigned long long>& done, F&& f) {
+  int dev = 0;
+  WISB_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(done.load(std::memory_order_acquire) & bit)) {
+    f();
+    done.fetch_or(bit, std::memory_order_release);
+  }
+}
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -556,10 +556,12 @@ void gemv_launch(const GemvArgs& a, int num_sms, cudaStream_t stream) {
   static_assert(GV_C * NR <= 32 && NR <= 16, "one lane per output");
   const GemvSmem L = gemv_smem_layout(a.R, a.K, LN);
   WISB_REQUIRE(L.total <= 220 * 1024, "gemv: activations do not fit in shared memory");
-  static int max_set = 0;
-  if (L.total > max_set) {
+  static std::atomic<int> max_set[64];  // per device (zero-initialised): largest size configured so far
+  int dev = 0;
+  WISB_CUDA(cudaGetDevice(&dev));
+  if (L.total > max_set[dev & 63].load()) {
     WISB_CUDA(cudaFuncSetAttribute(gemv_kernel<NR, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    max_set = L.total;
+    max_set[dev & 63].store(L.total);
   }
   const int tasks = cdiv(a.N, GV_COLS);
   const int per_sm = (220 * 1024) / (L.total + 1024) > 0 ? (220 * 1024) / (L.total + 1024) : 1;
@@ -575,11 +577,13 @@ void gemv_run(const GemvArgs& a, cudaStream_t stream) {
   WISB_REQUIRE(a.K % 32 == 0 && a.R >= 1 && a.R <= 8, "gemv: bad shape");
   WISB_REQUIRE((reinterpret_cast<uintptr_t>(a.w) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0, "gemv: operands must be 16-byte aligned");
   WISB_REQUIRE(a.ln_g == nullptr || a.K <= 1536, "gemv: LayerNorm prologue needs K <= 1536");
-  static int num_sms = 0;
+  static std::atomic<int> sms[64];  // per device
+  int dev = 0;
+  WISB_CUDA(cudaGetDevice(&dev));
+  int num_sms = sms[dev & 63].load();
   if (num_sms == 0) {
-    int dev = 0;
-    WISB_CUDA(cudaGetDevice(&dev));
     WISB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    sms[dev & 63].store(num_sms);
   }
   const bool ln = a.ln_g != nullptr;
   if (a.R <= 2) {
@@ -610,8 +614,8 @@ void dec_cross_attn_run(const float* q, const __half* k, const __half* v, float*
   WISB_REQUIRE(beam >= 1 && beam <= MAX_BEAM, "cross-attention: beam out of range");
   dim3 grid(H, n_utt, CA_CLUSTER);
   auto smem_for = [](int nb) { return 2 * CA_KEYS * HEAD_DIM * 2 + CA_GROUPS * nb * HEAD_DIM * 4; };
-  static std::once_flag once;
-  std::call_once(once, [&] {
+  static std::atomic<unsigned long long> once{0};
+  once_per_device(once, [&] {
     WISB_CUDA(cudaFuncSetAttribute(dec_cross_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(1)));
     WISB_CUDA(cudaFuncSetAttribute(dec_cross_attn_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(5)));
     WISB_CUDA(cudaFuncSetAttribute(dec_cross_attn_kernel<MAX_BEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(MAX_BEAM)));

@@ -380,8 +380,8 @@ enc_attn_ref_kernel(const __half* __restrict__ qkv, __half* __restrict__ ctx, in
 
 void conv1_gelu_run(const float* mel, const __half* w, const float* bias, __half* h1, int B, int d, cudaStream_t stream) {
   WISB_REQUIRE(d % C1_CT == 0, "conv1: d_model must be a multiple of 64");
-  static std::once_flag once;
-  std::call_once(once, [] {
+  static std::atomic<unsigned long long> once{0};
+  once_per_device(once, [] {
     WISB_CUDA(cudaFuncSetAttribute(conv1_gelu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C1_SMEM));
   });
   dim3 grid(cdiv(N_FRAMES, C1_FT), d / C1_CT, B);
@@ -412,8 +412,8 @@ void enc_attn_plan(AttnPlan& p, const __half* qkv, const __half* vt, __half* ctx
 }
 
 void enc_attn_run(const AttnPlan& p, cudaStream_t stream) {
-  static std::once_flag once;
-  std::call_once(once, [] {
+  static std::atomic<unsigned long long> once{0};
+  once_per_device(once, [] {
     WISB_CUDA(cudaFuncSetAttribute(enc_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
     WISB_CUDA(cudaFuncSetAttribute(enc_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
   });

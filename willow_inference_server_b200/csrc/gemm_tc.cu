@@ -397,8 +397,8 @@ void gemm_plan(GemmPlan& p, const __half* a, long long lda, const __half* w, int
 
 template <int BN, bool kMC>
 void gemm_launch(const GemmPlan& p, cudaStream_t stream) {
-  static std::once_flag once;
-  std::call_once(once, [] {
+  static std::atomic<unsigned long long> once{0};
+  once_per_device(once, [] {
     WISB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, kMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
   });
   cudaLaunchConfig_t cfg{};
