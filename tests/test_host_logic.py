@@ -54,6 +54,12 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/wisb200.h but not exported"
     assert sorted(_lib.EXPORTS) == declared  # the ctypes table binds exactly the header
     assert _lib.lib().wisb_abi_version() == 1
+    # ... with the same number of parameters per entry point as the C prototypes
+    flat = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    for name, params in re.findall(r"\b(wisb_[a-z_0-9]+)\s*\(([^)]*)\)\s*;", flat):
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_lib._SIGS[name][1]), (name, n, len(_lib._SIGS[name][1]))
 
 
 def test_storage_view_and_argument_errors():
