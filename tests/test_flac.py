@@ -109,3 +109,36 @@ def test_corruption_is_detected():
     assert audio.decode_flac(bytes(lying), verify=False)[0].shape == (4096,)
     with pytest.raises(ValueError, match="resampling"):
         audio.load_audio(fw.encode(x, blocks=[4096], sample_rate=44100))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_streams_roundtrip(seed):
+    # seeded fuzz over the writer's degrees of freedom: block sizes, widths, channel layouts, predictors, partitions
+    rng = np.random.default_rng(seed)
+    bps = int(rng.choice([8, 12, 16, 20, 24]))
+    ch = int(rng.choice([1, 2, 2, 3]))
+    blocks = [int(rng.choice([192, 256, 576, 1000, 1152, 4096, 17, 255, 257])) for _ in range(int(rng.integers(1, 6)))]
+    n = sum(blocks)
+    x = _signal(n, ch, bps, seed + 100)
+    modes, specs = [], []
+    for bs in blocks:
+        modes.append(str(rng.choice(["indep", "ls", "sr", "ms"])) if ch == 2 else "indep")
+        row = []
+        for _ in range(ch):
+            kind = str(rng.choice(["verbatim", "fixed", "fixed", "lpc"]))
+            po = int(rng.integers(0, 4))
+            while po > 0 and (bs % (1 << po) or (bs >> po) <= 8):
+                po -= 1
+            if kind == "fixed":
+                row.append({"kind": "fixed", "order": int(rng.integers(0, 5)), "po": po, "method": int(rng.integers(0, 2)),
+                            "escape": tuple(int(p) for p in range(1 << po) if rng.random() < 0.2)})
+            elif kind == "lpc":
+                order = int(rng.integers(1, 9))
+                prec = int(rng.integers(5, 13))
+                coefs = [int(c) for c in rng.integers(-(1 << (prec - 1)), 1 << (prec - 1), order) // order]
+                row.append({"kind": "lpc", "order": order, "coefs": coefs, "shift": prec - 1, "prec": prec, "po": po,
+                            "method": int(rng.integers(0, 2))})
+            else:
+                row.append({"kind": "verbatim"})
+        specs.append(row)
+    _roundtrip(x, bps=bps, blocks=blocks, stereo_modes=modes, specs=specs, md5=bool(seed % 2))
