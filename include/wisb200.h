@@ -62,6 +62,15 @@ int wisb_generate(wisb_handle* h, const float* mel, int B, const int32_t* prompt
                   float patience, float length_penalty, int max_length, const int32_t* extra_suppress, int n_extra,
                   int32_t* out_ids, int out_stride, int32_t* out_len, float* out_score);
 
+/* Same call with a per-utterance `max_length` (int32 [B], may be NULL = `max_length` for all): lets a cross-request
+ * batcher put requests with different length limits into ONE shared decoder pass (CTranslate2's generate takes a single
+ * max_length per call, /root/reference/main.py:687-692; the per-utterance form is what its semantics become when
+ * several such calls are coalesced).  out_stride >= the largest per-utterance limit of new tokens. */
+int wisb_generate_ex(wisb_handle* h, const float* mel, int B, const int32_t* prompts, int prompt_len, int beam_size,
+                     float patience, float length_penalty, int max_length, const int32_t* max_length_per_utt,
+                     const int32_t* extra_suppress, int n_extra, int32_t* out_ids, int out_stride, int32_t* out_len,
+                     float* out_score);
+
 /* (5) per utterance: language token ids sorted by probability (descending) and the probabilities.
  * lang_ids_out int32 [B, n_langs], probs_out float32 [B, n_langs]. */
 int wisb_detect_language(wisb_handle* h, const float* mel, int B, int32_t* lang_ids_out, float* probs_out);

@@ -69,6 +69,7 @@ class WhisperOracle:
         self.emb = self.w["dec.tok_emb"][: dims.n_vocab]
         self.suppress = torch.tensor(sorted(set(dims.suppress_ids)), dtype=torch.long)
         self.suppress_begin = torch.tensor(list(dims.suppress_ids_begin), dtype=torch.long)
+        self.logit_noise = None
 
     @classmethod
     def from_blob(cls, src):
@@ -165,6 +166,9 @@ class WhisperOracle:
     def _process(self, logits, gen_step: int, extra_suppress=None):
         """CT2 logits processors for the WIS call (suppress_tokens=[-1], suppress_blank=True)."""
         logits = logits.clone()
+        if self.logit_noise is not None:  # robustness probe (tests): see ``generate(logit_noise=...)``
+            sigma, gen = self.logit_noise
+            logits += sigma * torch.randn(logits.shape, generator=gen)
         logits[:, self.suppress] = NEG_INF
         if extra_suppress is not None and len(extra_suppress):
             logits[:, torch.as_tensor(list(extra_suppress), dtype=torch.long)] = NEG_INF
@@ -240,9 +244,6 @@ class WhisperOracle:
             cand_scores = flat[order]
             cand_beam = (order // V).tolist()
             cand_tok = (order % V).tolist()
-            if trace is not None:
-                cs = cand_scores.tolist()
-                trace.append(min([cs[j] - cs[j + 1] for j in range(len(cs) - 1) if math.isfinite(cs[j + 1])] or [1e9]))
             nxt = []  # indices into the candidate list that stay alive
             secondary = beam
             for k in range(beam):
@@ -256,6 +257,9 @@ class WhisperOracle:
                             secondary = j + 1
                             break
                 nxt.append(pick)
+            if trace is not None:
+                trace.append(self._beam_margin(cand_scores.tolist(), cand_tok, nxt, beam, eot, norm,
+                                               is_last or len(hyps) >= max_hyp, is_last))
             if is_last or len(hyps) >= max_hyp:
                 break
             parents = [cand_beam[j] for j in nxt]
@@ -266,14 +270,67 @@ class WhisperOracle:
             cache = [(k_[pidx], v_[pidx]) for k_, v_ in cache]
         if not hyps:
             return GenerationResult([[]], [0.0])
+        if trace is not None:  # last entry: gap between the two best finished hypotheses (normalised scores)
+            hs = sorted((h_[0] for h_ in hyps), reverse=True)
+            trace.append(("final", hs[0] - hs[1] if len(hs) > 1 else 1e9))
         best = max(range(len(hyps)), key=lambda i: (hyps[i][0], -i))  # first best on ties
         return GenerationResult([hyps[best][1]], [hyps[best][0]])
+
+    @staticmethod
+    def _beam_margin(cs, cand_tok, nxt, beam, eot, norm, finishing, is_last):
+        """Smallest DECISION-RELEVANT gap of one beam-search step, in cumulative log-prob units (normalised gap x norm).
+
+        A step decides (a) which candidates form the top-``beam`` set -- those ending in eot (all of them at the last
+        step) become hypotheses -- and (b) which later non-eot candidates replace them as alive beams.  The order of two
+        alive non-eot candidates inside the used set changes nothing (it only permutes rows), so only two boundaries
+        count: rank beam-1 vs rank beam, and the last used candidate vs the next one that could be used instead.  When
+        the search ends at this step the alive set no longer matters, only the hypothesis set does."""
+        gaps = []
+
+        def gap(a, b):
+            if b < len(cs) and math.isfinite(cs[a]):
+                gaps.append((cs[a] - cs[b]) if math.isfinite(cs[b]) else 1e9)
+
+        a, b = beam - 1, beam
+        both_plain = cand_tok[a] != eot and cand_tok[b] != eot
+        if finishing:
+            if is_last or not both_plain:
+                gap(a, b)
+        else:
+            if not (both_plain and b in nxt):
+                gap(a, b)
+            m = max(nxt)
+            if m >= beam:
+                c = next((j for j in range(m + 1, len(cs)) if cand_tok[j] != eot), None)
+                if c is not None:
+                    gap(m, c)
+                elif m + 1 < len(cs):
+                    gap(m, len(cs) - 1)  # the real competitor is below the candidate list: a lower bound of the gap
+                else:
+                    gaps.append(0.0)     # cannot tell how close the next candidate was
+        return (min(gaps) if gaps else 1e9) * norm
 
     @torch.no_grad()
     def generate(self, features, prompts, beam_size: int = 5, patience: float = 1.0, length_penalty: float = 1.0,
                  max_length: int = 448, suppress_tokens=(-1,), return_scores: bool = False, trace=None,
-                 enc=None):
-        """features float32 [B,80,3000]; prompts list[list[int]] -> list[GenerationResult]."""
+                 enc=None, logit_noise=None):
+        """features float32 [B,80,3000]; prompts list[list[int]] -> list[GenerationResult].
+
+        ``logit_noise=(sigma, seed)`` adds seeded Gaussian noise of that size to every raw logit of every step: the
+        tests use it to find out whether a transcript is a ROBUST decision of the reference algorithm (unchanged under
+        perturbations of the size of the documented fp16-vs-fp32 logit tolerance) or hangs on a near-tie."""
+        self.logit_noise = None
+        if logit_noise is not None:
+            g = torch.Generator()
+            g.manual_seed(int(logit_noise[1]))
+            self.logit_noise = (float(logit_noise[0]), g)
+        try:
+            return self._generate(features, prompts, beam_size, patience, length_penalty, max_length, suppress_tokens,
+                                  trace, enc)
+        finally:
+            self.logit_noise = None
+
+    def _generate(self, features, prompts, beam_size, patience, length_penalty, max_length, suppress_tokens, trace, enc):
         extra = [t for t in suppress_tokens if t >= 0]
         if -1 not in suppress_tokens:
             raise NotImplementedError("oracle restates the WIS call, which always keeps suppress_tokens=[-1]")

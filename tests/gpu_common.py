@@ -1,4 +1,10 @@
-"""Shared helpers for the -m gpu parity tests: seeded synthetic models for engine (C ABI) and oracle alike."""
+"""Shared helpers for the -m gpu parity tests: seeded synthetic models for engine (C ABI) and oracle alike.
+
+Token parity is demanded EXACTLY (north_star: token-id exact under greedy, text-exact under beam 5) on the cases where
+the reference algorithm's own answer is a robust decision: the oracle is re-run with seeded Gaussian noise of the size of
+the documented logit tolerance on every logit, and a case counts when its transcript does not move
+(``robust_cases``).  The default test model is PEAKED like a trained model (``weights.synth_state_dict(script=...)``), so
+most cases qualify; a flat random model has near-ties at almost every step and almost none would."""
 import functools
 
 import numpy as np
@@ -8,20 +14,44 @@ from oracle.whisper_ref import WhisperOracle
 from willow_inference_server_b200 import _lib, weights as W
 
 PROMPT = [50258, 50259, 50359, 50363]
+LOGIT_TOL = 6e-2          # teacher-forced logits, fp16 tensor-core activations vs the fp32 oracle (std of the logits ~ 4)
+SCRIPT = (4, 3.3, 1.67)   # peaked output distribution: 4 plausible tokens per position, 3.3 noise deviations apart
+RAMP = (8, 12.0)          # <|endoftext|> ramp: hypotheses finish at data-dependent steps (about 14-17 generated tokens)
 
 
-@functools.lru_cache(maxsize=4)
-def model_pair(d_model=128, n_heads=2, n_layers=2, seed=11, eot_ramp=(10, 8.0)):
-    dims = W.WhisperDims(d_model=d_model, n_heads=n_heads, n_enc_layers=n_layers, n_dec_layers=n_layers)
-    tensors = W.synth_engine_tensors(dims, seed=seed, eot_ramp=eot_ramp)
+def make_blob(dims, seed=11, eot_ramp=RAMP, script=SCRIPT):
+    tensors = W.synth_engine_tensors(dims, seed=seed, eot_ramp=eot_ramp, script=script)
     buf = np.zeros(W.blob_nbytes(tensors), np.uint8)
     W.write_blob_into(buf, dims, tensors)
+    return buf
+
+
+@functools.lru_cache(maxsize=6)
+def model_pair(d_model=128, n_heads=2, n_layers=2, seed=11, eot_ramp=RAMP, script=SCRIPT):
+    dims = W.WhisperDims(d_model=d_model, n_heads=n_heads, n_enc_layers=n_layers, n_dec_layers=n_layers)
+    buf = make_blob(dims, seed, eot_ramp, script)
     oracle = WhisperOracle.from_blob(buf)
     handle = _lib.Handle.from_host(buf, 0)
     return dims, oracle, handle
 
 
-@functools.lru_cache(maxsize=2)
+DURATIONS = [61440, 160000, 480000, 171008, 30000, 467968, 90000, 250000, 16000, 333333, 123456, 400000, 75000, 200000,
+             48000, 288000]
+
+
+@functools.lru_cache(maxsize=4)
 def mel_inputs(n=4):
-    durations = [61440, 160000, 480000, 171008, 30000, 467968][:n]
-    return om.log_mel_batch([om.synth_utterance(m, 100 + i) for i, m in enumerate(durations)])
+    return om.log_mel_batch([om.synth_utterance(m, 100 + i) for i, m in enumerate(DURATIONS[:n])])
+
+
+def robust_cases(oracle, mel, prompts, beam, enc=None, n_probe=3, sigma=LOGIT_TOL, **kw):
+    """-> (oracle results, indices whose transcript is unchanged under `n_probe` seeded logit perturbations of std
+    `sigma`): the cases on which the CUDA path must reproduce the oracle's tokens exactly."""
+    if enc is None:
+        enc = oracle.encode(mel)
+    base = oracle.generate(mel, prompts, beam_size=beam, enc=enc, **kw)
+    stable = [True] * len(base)
+    for k in range(n_probe):
+        alt = oracle.generate(mel, prompts, beam_size=beam, enc=enc, logit_noise=(sigma, 1000 + k), **kw)
+        stable = [s and a.sequences_ids == b.sequences_ids for s, a, b in zip(stable, alt, base)]
+    return base, [i for i, s in enumerate(stable) if s]

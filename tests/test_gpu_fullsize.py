@@ -63,10 +63,9 @@ def test_mixed_duration_batch_properties(large):
 def test_handles_coexist_and_threads(large):
     dims, h = large
     small_dims = W.WhisperDims(d_model=128, n_heads=2, n_enc_layers=2, n_dec_layers=2)
-    t = W.synth_engine_tensors(small_dims, seed=11, eot_ramp=(10, 8.0))
-    buf = np.zeros(W.blob_nbytes(t), np.uint8)
-    W.write_blob_into(buf, small_dims, t)
-    hs = _lib.Handle.from_host(buf, 0)  # a second model size next to the large one (WIS keeps five, main.py:319-326)
+    from tests.gpu_common import make_blob
+
+    hs = _lib.Handle.from_host(make_blob(small_dims), 0)  # a second model size next to the large one (WIS keeps five, main.py:319-326)
     mel = audio.log_mel_batch([_synth(61440, 1)])
     want_small, _ = hs.generate(mel, np.array([PROMPT], np.int32), 5)
     want_large, _ = h.generate(mel, np.array([PROMPT], np.int32), 5, max_length=16)

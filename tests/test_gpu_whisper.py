@@ -3,17 +3,17 @@
 Tolerances (north_star: token-id exact under greedy, text-exact under beam=5):
   * encoder output (after the final LayerNorm, O(1) values): fp16 tensor-core inputs, fp32 accumulation -> <= 3e-2 abs
   * teacher-forced logits (std ~4): <= 6e-2 abs
-  * token ids: exact whenever the oracle's decision margins exceed the logit tolerance (checked per case)
+  * token ids: EXACT on every case whose oracle transcript is a robust decision (tests/gpu_common.robust_cases); the
+    tests also require that most cases are robust, so the comparison cannot become vacuous
 """
 import numpy as np
 import pytest
 
-from tests.gpu_common import PROMPT, mel_inputs, model_pair
+from tests.gpu_common import LOGIT_TOL, PROMPT, mel_inputs, model_pair, robust_cases
 from willow_inference_server_b200 import models
 
 pytestmark = pytest.mark.gpu
 ENC_TOL = 3e-2
-LOGIT_TOL = 6e-2
 
 
 @pytest.fixture(scope="module")
@@ -62,38 +62,21 @@ def test_forced_logits_match_oracle(pair):
     assert np.abs(got - want).max() <= LOGIT_TOL
 
 
-def _explained_mismatches(got, res, traces, thin):
-    """Token lists must be identical unless the oracle itself reports a thin decision margin at the first step where
-    they part ways (fp16 tensor-core activations vs the fp32 oracle can flip a near-tie; everything before it must
-    still agree).  Returns the number of such explained mismatches."""
-    bad = 0
-    for g, r, tr in zip(got, res, traces):
-        want = r.sequences_ids[0]
-        if g == want:
-            continue
-        k = next((i for i, (a, b) in enumerate(zip(g, want)) if a != b), min(len(g), len(want)))
-        assert tr[min(k, len(tr) - 1)] < thin or min(tr[: k + 1]) < thin, (k, g, want, tr)
-        bad += 1
-    return bad
-
-
 @pytest.mark.parametrize("beam", [1, 5, 2])
 def test_generate_matches_oracle(pair, beam):
     dims, oracle, h = pair
-    mel = mel_inputs(4)
+    mel = mel_inputs(6)
     n = mel.shape[0]
-    enc = oracle.encode(mel)
-    trace = []
-    res = oracle.generate(mel, [PROMPT] * n, beam_size=beam, enc=enc, trace=trace)
+    res, robust = robust_cases(oracle, mel, [PROMPT] * n, beam)
+    assert len(robust) >= 4, f"only {len(robust)} of {n} oracle transcripts are robust decisions"
     m = models.Whisper(None, device="cuda", _handles=[h])
     out = m.generate(models.StorageView.from_array(mel), [PROMPT] * n, beam_size=beam, return_scores=True)
-    got = [o.sequences_ids[0] for o in out]
-    # greedy: margin = top-1 minus top-2 logit at each step; beam: smallest gap between consecutive candidates
-    bad = _explained_mismatches(got, res, trace, 2 * LOGIT_TOL)
-    assert bad <= 1, f"{bad} of {n} transcripts differ from the oracle"
-    for o, r in zip(out, res):
-        if o.sequences_ids[0] == r.sequences_ids[0] and beam > 1:
-            assert abs(o.scores[0] - r.scores[0]) < 5e-2
+    for i in robust:  # exact token parity, no tolerated mismatch
+        assert out[i].sequences_ids[0] == res[i].sequences_ids[0], (beam, i)
+        if beam > 1:
+            assert abs(out[i].scores[0] - res[i].scores[0]) < 5e-2
+    assert len({tuple(res[i].sequences_ids[0]) for i in robust}) >= 3  # the transcripts depend on the audio
+    for o in out:
         assert dims.eot not in o.sequences_ids[0]
         assert not set(o.sequences_ids[0]) & set(dims.suppress_ids)
 
@@ -129,10 +112,13 @@ def test_max_length_and_suppress(pair):
     for beam in (1, 3):
         ids, _ = h.generate(mel, [PROMPT], beam_size=beam, max_length=24, extra_suppress=[dims.eot])
         assert len(ids[0]) == 12
-        want = oracle.generate(mel, [PROMPT], beam_size=beam, max_length=24, suppress_tokens=(-1, dims.eot))
-        assert ids[0] == want[0].sequences_ids[0] or beam > 1
-    ids, _ = h.generate(mel, [PROMPT], beam_size=1)  # mask restored
-    assert len(ids[0]) != 12 or True
+        want, robust = robust_cases(oracle, mel, [PROMPT], beam, max_length=24, suppress_tokens=(-1, dims.eot))
+        assert len(want[0].sequences_ids[0]) == 12
+        if robust:
+            assert ids[0] == want[0].sequences_ids[0]
+    ids, _ = h.generate(mel, [PROMPT], beam_size=1)  # mask restored: <|endoftext|> ends the transcript again
+    assert ids[0] == h.generate(mel, [PROMPT], beam_size=1, extra_suppress=[])[0][0]
+    assert ids[0] != h.generate(mel, [PROMPT], beam_size=1, extra_suppress=[dims.eot])[0][0]
 
 
 def test_detect_language(pair):
@@ -141,12 +127,16 @@ def test_detect_language(pair):
     m = models.Whisper(None, device="cuda", _handles=[h])
     got = m.detect_language(models.StorageView.from_array(mel))
     want = oracle.detect_language(mel)
+    from willow_inference_server_b200.languages import LANGUAGE_CODES
+
     for g, w in zip(got, want):
         assert len(g) == 99 and g[0][0].startswith("<|")
         assert abs(sum(p for _, p in g) - 1) < 1e-4
-        wp = dict(w)
-        top = g[0]
-        assert abs(top[1] - max(wp.values())) < 2e-2
+        # the detected language (WIS reads results[0][0], main.py:640) and the next two are the oracle's
+        want_top = [f"<|{LANGUAGE_CODES[t - dims.lang_first]}|>" for t, _ in w[:3]]
+        assert [t for t, _ in g[:3]] == want_top
+        for (_, pg), (_, pw) in zip(g[:3], w[:3]):
+            assert abs(pg - pw) < 2e-2
 
 
 def test_argument_errors(pair):
@@ -166,16 +156,17 @@ def test_argument_errors(pair):
 
 
 def test_wider_model_batch(pair):
-    # d=256, 4 heads, 3 layers: exercises multi-head indexing, BN=256 tiles and mini-batched decoding (7 utterances)
-    dims, oracle, h = model_pair(256, 4, 3, 5, (12, 8.0))
-    mel = np.concatenate([mel_inputs(4), mel_inputs(4)[:3]])
+    # d=256, 4 heads, 3 layers: exercises multi-head indexing, BN=256 tiles and a 7-utterance batch (35 rows: the
+    # batched decoder pass)
+    dims, oracle, h = model_pair(256, 4, 3, 5)
+    mel = np.concatenate([mel_inputs(6)[:4], mel_inputs(6)[:3]])
     want = oracle.encode(mel[:2]).numpy()
     assert np.abs(h.debug_encode(mel[:2]) - want).max() <= ENC_TOL
-    trace = []
-    res = oracle.generate(mel, [PROMPT] * 7, beam_size=5, trace=trace)
+    res, robust = robust_cases(oracle, mel, [PROMPT] * 7, 5)
+    assert len(robust) >= 5
     got, _ = h.generate(mel, [PROMPT] * 7, beam_size=5)
-    agree = sum(g == r.sequences_ids[0] for g, r in zip(got, res))
-    assert agree >= 6
+    for i in robust:
+        assert got[i] == res[i].sequences_ids[0], i
     assert got[0] == got[4] and got[1] == got[5]  # same audio -> same transcript regardless of batch position
 
 
@@ -185,8 +176,12 @@ def test_encoder_cache_detect_then_generate(pair):
     mel = mel_inputs(4)[:1].copy()
     plain = models.Whisper(None, device="cuda", _handles=[h])
     want = plain.generate(models.StorageView.from_array(mel), [PROMPT], beam_size=5)[0].sequences_ids[0]
+    ores, orobust = robust_cases(oracle, mel, [PROMPT], 5)
+    if orobust:
+        assert want == ores[0].sequences_ids[0]  # checked against the oracle, not only against the engine itself
     want_lang = plain.detect_language(models.StorageView.from_array(mel))
-    assert plain.timing()["encoder_ms"] >= 0.0
+    assert [t for t, _ in want_lang[0]][0] == "<|%s|>" % __import__("willow_inference_server_b200.languages", fromlist=["x"]).LANGUAGE_CODES[
+        oracle.detect_language(mel)[0][0][0] - dims.lang_first]
     m = models.Whisper(None, device="cuda", _handles=[h], reuse_encoder=True)
     try:
         langs = m.detect_language(models.StorageView.from_array(mel))
@@ -204,7 +199,6 @@ def test_encoder_cache_detect_then_generate(pair):
         mel2[0, 3, 100] += 0.5                                   # one changed feature: the cache must miss
         other = m2.generate(models.StorageView.from_array(mel2), [PROMPT], beam_size=5)[0].sequences_ids[0]
         assert m2.timing()["encoder_ms"] > 0.05
-        assert other == oracle.generate(mel2, [PROMPT], beam_size=5)[0].sequences_ids[0] or True
         again = m2.generate(models.StorageView.from_array(mel), [PROMPT], beam_size=5)[0].sequences_ids[0]
         assert again == want and m2.timing()["encoder_ms"] > 0.05   # different features in between: re-encoded
     finally:
@@ -240,10 +234,9 @@ def test_two_replicas_in_one_process():
     from willow_inference_server_b200 import _lib, weights as W
 
     dims, oracle, h0 = model_pair()
-    tensors = W.synth_engine_tensors(dims, seed=11, eot_ramp=(10, 8.0))
-    buf = np.zeros(W.blob_nbytes(tensors), np.uint8)
-    W.write_blob_into(buf, dims, tensors)
-    h1 = _lib.Handle.from_host(buf, 1)
+    from tests.gpu_common import make_blob
+
+    h1 = _lib.Handle.from_host(make_blob(dims), 1)
     mel = mel_inputs(4)
     one = models.Whisper(None, device="cuda", _handles=[h0])
     want = [r.sequences_ids[0] for r in one.generate(models.StorageView.from_array(mel), [PROMPT] * 4, beam_size=5)]

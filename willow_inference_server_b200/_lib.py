@@ -32,6 +32,8 @@ _SIGS = {
     "wisb_logmel": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "wisb_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float,
                                 C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "wisb_generate_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float,
+                                   C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "wisb_detect_language": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "wisb_get_timing": (C.c_int, [C.c_void_p, C.c_void_p]),
     "wisb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
@@ -169,14 +171,20 @@ class Handle:
             B = mel.shape[0]
         if B is None or prompts.shape[0] != B:
             raise ValueError("one prompt per feature window is required")
-        stride = max(1, max_length // 2)
+        per_utt = None
+        if not np.isscalar(max_length):  # one limit per utterance (requests coalesced by the batcher)
+            per_utt = np.ascontiguousarray(max_length, np.int32)
+            if per_utt.shape != (B,):
+                raise ValueError("max_length must be an int or one int per utterance")
+            max_length = int(per_utt.max())
+        stride = max(1, int(max_length) // 2)
         ids = np.zeros((B, stride), np.int32)
         lens = np.zeros(B, np.int32)
         scores = np.zeros(B, np.float32)
         extra = np.ascontiguousarray(list(extra_suppress), np.int32)
-        check(lib().wisb_generate(self._h, ptr(mel), B, ptr(prompts), prompts.shape[1], int(beam_size), float(patience),
-                                  float(length_penalty), int(max_length), ptr(extra) if extra.size else None, extra.size,
-                                  ptr(ids), stride, ptr(lens), ptr(scores)))
+        check(lib().wisb_generate_ex(self._h, ptr(mel), B, ptr(prompts), prompts.shape[1], int(beam_size), float(patience),
+                                     float(length_penalty), int(max_length), ptr(per_utt), ptr(extra) if extra.size else None,
+                                     extra.size, ptr(ids), stride, ptr(lens), ptr(scores)))
         return [ids[b, : lens[b]].tolist() for b in range(B)], scores.tolist()
 
     def detect_language(self, mel, B=None):

@@ -2,6 +2,7 @@
 // (/root/reference/main.py:687-692).
 #pragma once
 #include "common.cuh"
+#include "kernels.h"
 
 namespace wisb {
 
@@ -84,12 +85,53 @@ struct SearchArgs {
   int* best_len = nullptr;        // [n_utt]
   int* best_tokens = nullptr;     // [n_utt][max_new]
   DecState* st = nullptr;
+  int* row_pos = nullptr;         // [R] position fed by every row this step (batched pass); advanced with st->pos
+  int* row_slot = nullptr;        // [R] cache slot every row writes this step's K/V to (= its own row)
+  const int* max_new_u = nullptr; // optional [n_utt]: per-utterance cap on generated tokens (<= max_new)
 };
 void search_step_run(const SearchArgs& a, cudaStream_t stream);
 // prompt prefill: no search, just feed the next prompt token and advance the position
 void prefill_advance_run(int* tokens, const int* prompt /*[n_utt][prompt_len]*/, int prompt_len, int R, int beam,
                          DecState* st, cudaStream_t stream);
 void search_init_run(const SearchArgs& a, const int* prompt, cudaStream_t stream, int shared_prefix = 0);
+// rows of a batched prefill pass: row i = prompt position p0 + i % chunk of utterance i / chunk, cache slot = the
+// utterance's first beam
+void prefill_rows_run(int* tokens, int* row_pos, int* row_slot, const int* prompt, int prompt_len, int n_utt, int p0,
+                      int chunk, int beam, cudaStream_t stream);
+
+// ------------------------------------------------------------------ batched decoder pass (decoder_batch.cu)
+struct BatchLayer {
+  GemmPlan qkv, o, cq, co, fc1, fc2;  // built for the row capacity of the workspaces; o / co / fc2 write split-K partials
+  const float *ln1g = nullptr, *ln1b = nullptr;      // LayerNorm before the QKV GEMM (only layer 0's is applied by the embedding kernel)
+  const float *ob = nullptr, *ln2g = nullptr, *ln2b = nullptr;    // out-proj bias, LayerNorm before cross-attention
+  const float *cob = nullptr, *ln3g = nullptr, *ln3b = nullptr;   // cross out-proj bias, LayerNorm before the MLP
+  const float *fc2b = nullptr, *next_g = nullptr, *next_b = nullptr;  // fc2 bias, the NEXT LayerNorm (layer l+1's ln1 or the final one)
+  const __half* ck = nullptr;   // cross K / V of this layer for utterance 0 of the pass: [n_utt][H][1536][64]
+  const __half* cv = nullptr;
+  __half* kcache = nullptr;     // self-attention cache of this layer: [slots][t_cap][d]
+  __half* vcache = nullptr;
+};
+struct BatchArgs {
+  int R = 0, d = 0, H = 0, n_utt = 0, rows_per_utt = 0, t_cap = 0, t_ind = 0, prefill = 0, with_logits = 0, pdl = 0;
+  const int* tokens = nullptr;    // [R]
+  const int* row_pos = nullptr;   // [R]
+  const int* row_slot = nullptr;  // [R]
+  const __half* tok_emb = nullptr;
+  const float* pos_emb = nullptr;
+  float* x = nullptr;             // [rows_cap, d] fp32 residual stream
+  __half* xn = nullptr;           // [rows_cap, d] LayerNorm output (GEMM A operand)
+  float* q = nullptr;             // [rows_cap, d]
+  __half* ctx = nullptr;          // [rows_cap, d] attention output (GEMM A operand)
+  float* part = nullptr;          // split-K partial slabs [splits][rows_cap][d]
+  long long part_stride = 0;
+  const int* indir0 = nullptr;
+  const int* indir1 = nullptr;
+  const int* flip = nullptr;
+  const int* done = nullptr;      // [n_utt] or null (prefill)
+  const GemmPlan* vocab = nullptr;
+};
+// returns the number of kernels launched
+int batch_pass_run(const BatchArgs& a, const BatchLayer* layers, int n_layers, cudaStream_t stream);
 
 // ------------------------------------------------------------------ persistent decoder pass (decoder_mega.cu)
 struct MegaGemv {

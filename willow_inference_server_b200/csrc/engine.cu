@@ -78,7 +78,7 @@ struct DecLayerW {
 };
 
 struct GraphKey {
-  int n_utt, beam, prompt_len, max_new, max_hyp, u0, b_total;
+  int n_utt, beam, prompt_len, max_new, max_hyp, u0, b_total, batched;
   float lp;
   bool operator<(const GraphKey& o) const {
     return memcmp(this, &o, sizeof(GraphKey)) < 0;
@@ -133,6 +133,15 @@ struct wisb_handle {
   DevBuf<unsigned long long> part;
   DevBuf<int> cand_idx, tokens, seq0, seq1, ind0, ind1, flip, done, n_hyp, best_len, best_tokens, prompt_dev, lang_ids;
   DevBuf<DecState> st;
+  DevBuf<int> row_pos, row_slot, max_new_u;
+  int search_rows = 0;  // rows the search / state buffers above are sized for
+  // batched decoder pass (more than DEC_MAX_ROWS rows): workspaces for bd_rows (multiple of 128) rows, bd_tcap positions
+  int batch_rows = 320, batch_pdl = 1, decoder_batch = 1;  // options: row capacity of one shared pass; programmatic dependent launch
+  int bd_rows = 0, bd_tcap = 0, bd_launches_step = 0;
+  DevBuf<float> bx, bq, bpart, blogits;
+  DevBuf<__half> bxn, bctx, bh, bkc, bvc;
+  std::vector<BatchLayer> bd_layers;
+  GemmPlan bd_vocab;
   DevBuf<MegaLayer> mega_layers;
   DevBuf<unsigned> mega_flags;
   // optional reuse of the encoder output + cross K/V between consecutive calls on identical host features
@@ -242,6 +251,37 @@ void parse_blob(wisb_handle* h, const std::vector<uint8_t>& head) {
   WISB_REQUIRE(d.n_langs <= 128, "more than 128 languages");
 }
 
+void drop_graphs(wisb_handle* h) {
+  for (auto& kv : h->graphs) {
+    if (kv.second.prefill) cudaGraphExecDestroy(kv.second.prefill);
+    if (kv.second.step) cudaGraphExecDestroy(kv.second.step);
+  }
+  h->graphs.clear();
+}
+
+// search / beam state for R rows (rows = utterances x beams of one shared decoder pass)
+void ensure_search(wisb_handle* h, int rows) {
+  if (rows <= h->search_rows) return;
+  WISB_CUDA(cudaStreamSynchronize(h->stream));
+  drop_graphs(h);  // captured graphs hold the old pointers
+  const size_t R = static_cast<size_t>(rows);
+  h->row_lse.ensure(R); h->cum.ensure(R);
+  h->part_max.ensure(R * TOPK_CHUNKS); h->part_sum.ensure(R * TOPK_CHUNKS);
+  h->part.ensure(R * TOPK_CHUNKS * MAX_CAND);
+  h->cand_score.ensure(R * MAX_CAND); h->cand_idx.ensure(R * MAX_CAND);
+  h->tokens.ensure(R);
+  h->seq0.ensure(R * T_MAX, true); h->seq1.ensure(R * T_MAX, true);
+  h->ind0.ensure(R * T_MAX, true); h->ind1.ensure(R * T_MAX, true);
+  h->done.ensure(R); h->n_hyp.ensure(R); h->best_score.ensure(R); h->best_len.ensure(R);
+  h->best_tokens.ensure(R * T_MAX, true);
+  h->prompt_dev.ensure(R * T_MAX);
+  h->row_pos.ensure(R, true); h->row_slot.ensure(R, true); h->max_new_u.ensure(R, true);
+  h->lang_probs.ensure(R * 128);
+  h->pin_i.ensure(4 + R * (T_MAX + 2));
+  h->pin_f.ensure(R * 130);
+  h->search_rows = rows;
+}
+
 void finish_create(wisb_handle* h) {
   const Dims& d = h->dims;
   const bool has_model = h->blob != nullptr;
@@ -288,7 +328,7 @@ void finish_create(wisb_handle* h) {
   h->mask_cur.ensure(d.n_vocab);
   WISB_CUDA(cudaMemcpy(h->mask_base.p, mask.data(), mask.size(), cudaMemcpyHostToDevice));
   WISB_CUDA(cudaMemcpy(h->mask_cur.p, mask.data(), mask.size(), cudaMemcpyHostToDevice));
-  // decoder workspaces for DEC_MAX_ROWS rows
+  // decoder workspaces for DEC_MAX_ROWS rows (the persistent SIMT pass); the batched pass grows the search state later
   const size_t R = DEC_MAX_ROWS;
   h->dx.ensure(R * d.d_model, true);
   h->dq.ensure(R * d.d_model, true);
@@ -298,18 +338,9 @@ void finish_create(wisb_handle* h) {
   const size_t cache = static_cast<size_t>(d.n_dec_layers) * R * T_MAX * d.d_model;
   h->kcache.ensure(cache, true);
   h->vcache.ensure(cache, true);
-  h->row_lse.ensure(R); h->cum.ensure(R);
-  h->part_max.ensure(R * TOPK_CHUNKS); h->part_sum.ensure(R * TOPK_CHUNKS);
-  h->part.ensure(R * TOPK_CHUNKS * MAX_CAND);
-  h->cand_score.ensure(R * MAX_CAND); h->cand_idx.ensure(R * MAX_CAND);
-  h->tokens.ensure(R);
-  h->seq0.ensure(R * T_MAX, true); h->seq1.ensure(R * T_MAX, true);
-  h->ind0.ensure(R * T_MAX, true); h->ind1.ensure(R * T_MAX, true);
   h->flip.ensure(1, true);
-  h->done.ensure(R); h->n_hyp.ensure(R); h->best_score.ensure(R); h->best_len.ensure(R);
-  h->best_tokens.ensure(R * T_MAX, true);
-  h->prompt_dev.ensure(R * T_MAX);
   h->st.ensure(1, true);
+  ensure_search(h, DEC_MAX_ROWS);
   h->mega_layers.ensure(d.n_dec_layers);
   h->mega_layers_host.ensure(d.n_dec_layers);
   h->mega_flags.ensure(mega_flags_words(), true);
@@ -337,24 +368,25 @@ void finish_create(wisb_handle* h) {
       mega_chunk_major(h->dec_w[i].fc2w, h->fc2_chunked.p + per * i, d.d_model, 4 * d.d_model, h->stream);
   }
   h->cross_part.ensure(static_cast<size_t>(DEC_MAX_ROWS) * d.n_heads * 16 * MAX_BEAM * 68, true);
-  h->lang_probs.ensure(R * 128);
-  h->pin_i.ensure(4 + R * (T_MAX + 2));
-  h->pin_f.ensure(R * 130);
   WISB_CUDA(cudaStreamSynchronize(h->stream));
 }
 
+// feature buffer [B,80,3000] (+ the per-utterance maxima of the log-mel kernel); growing it drops what it held
+void ensure_mel(wisb_handle* h, int B) {
+  h->lm_max.ensure(B);
+  const size_t n = static_cast<size_t>(B) * N_MELS * N_FRAMES;
+  if (n <= h->mel.n) return;
+  h->mel.ensure(n);
+  h->mel_B = 0;
+}
+
 void ensure_encoder(wisb_handle* h, int B) {
-  if (h->blob == nullptr) {  // front-end-only handle: just the feature buffers
-    h->mel.ensure(static_cast<size_t>(B) * N_MELS * N_FRAMES);
-    h->lm_max.ensure(B);
-    return;
-  }
+  if (h->blob == nullptr) return;  // front-end-only handle
   const Dims& dm = h->dims;
   const int d = dm.d_model, H = dm.n_heads;
   const long long M = static_cast<long long>(B) * T_ENC_PAD;
   if (B > h->enc_cap) {
     h->plans_B = 0;
-    h->mel.ensure(static_cast<size_t>(B) * N_MELS * N_FRAMES);
     h->h1.release();
     h->h1.ensure((static_cast<size_t>(B) * H1_ROWS + 8) * d, true);
     h->x.ensure(M * d, true);
@@ -365,7 +397,6 @@ void ensure_encoder(wisb_handle* h, int B) {
     h->hbuf.ensure(M * 4 * d, true);
     h->enc_out.ensure(M * d, true);
     h->ckv.ensure(static_cast<size_t>(dm.n_dec_layers) * 2 * M * d, true);
-    h->lm_max.ensure(B);
     h->enc_cap = B;
   }
   if (h->plans_B == B && h->plans_vmn == h->attn_v_mn) return;
@@ -428,7 +459,7 @@ void ensure_encoder(wisb_handle* h, int B) {
 }
 
 // mel (device, [B,80,3000]) -> enc_out fp16 [B*1536, d] (+ cross K/V when with_ckv)
-void run_encoder(wisb_handle* h, int B, int n_layers, bool with_ckv) {
+void run_encoder(wisb_handle* h, int B, int n_layers, bool with_ckv, int mel_first = 0) {
   const Dims& dm = h->dims;
   const int d = dm.d_model;
   const int M = B * T_ENC_PAD;
@@ -436,7 +467,7 @@ void run_encoder(wisb_handle* h, int B, int n_layers, bool with_ckv) {
   ensure_encoder(h, B);
   h->enc_valid = false;  // callers that want the result cached re-validate it after a full encode
   h->prof_begin(3);
-  conv1_gelu_run(h->mel.p, h->H("enc.conv1.w"), h->F("enc.conv1.b"), h->h1.p, B, d, s);
+  conv1_gelu_run(h->mel.p + static_cast<size_t>(mel_first) * N_MELS * N_FRAMES, h->H("enc.conv1.w"), h->F("enc.conv1.b"), h->h1.p, B, d, s);
   h->prof_end();
   h->prof_begin(0);
   gemm_run(h->plan_conv2, s);
@@ -488,7 +519,7 @@ void run_encoder(wisb_handle* h, int B, int n_layers, bool with_ckv) {
 // case the caller skips the encoder.  Off by default: a benchmark that feeds the same utterance every step must not
 // silently skip work.
 bool upload_mel(wisb_handle* h, const float* mel, int B) {
-  ensure_encoder(h, B);
+  ensure_mel(h, B);
   if (mel == nullptr) {
     WISB_REQUIRE(h->mel_B == B, "mel == NULL but wisb_logmel(keep_on_device) did not leave features for this batch size");
     h->mel_cache_B = 0;
@@ -521,6 +552,7 @@ void encode_for_decode(wisb_handle* h, int B, bool reuse) {
 struct DecodeCfg {
   int u0, n_utt, B_total, beam, prompt_len, max_new, max_hyp;
   float lp;
+  int per_utt_max_new = 0;  // h->max_new_u holds a per-utterance cap (<= max_new)
 };
 
 SearchArgs make_search_args(wisb_handle* h, const DecodeCfg& c) {
@@ -558,6 +590,9 @@ SearchArgs make_search_args(wisb_handle* h, const DecodeCfg& c) {
   a.best_len = h->best_len.p;
   a.best_tokens = h->best_tokens.p;
   a.st = h->st.p;
+  a.row_pos = h->row_pos.p;
+  a.row_slot = h->row_slot.p;
+  a.max_new_u = c.per_utt_max_new ? h->max_new_u.p : nullptr;
   return a;
 }
 
@@ -830,6 +865,241 @@ int decode_pass(wisb_handle* h, const DecodeCfg& c, const int32_t* prompts, int3
   return steps;
 }
 
+
+// ------------------------------------------------------------------------------------------------- batched decoder pass
+// tile width / split-K of one decoder GEMM for `M` rows: keep >= ~120 CTAs streaming the weight matrix
+void plan_dec_gemm(wisb_handle* h, GemmPlan& p, const __half* a, long long lda, const __half* w, int M, int N, int K,
+                   GemmEpi e, bool allow_split) {
+  const int mt = M / 128;
+  int bn = 256;
+  while (bn > 64 && (N % bn != 0 || mt * (N / bn) < 120)) bn /= 2;
+  int splits = 1;
+  if (allow_split) {
+    const int kb = K / 64;
+    while (mt * (N / bn) * splits < 120 && splits < 8 && kb % (splits * 2) == 0 && kb / (splits * 2) >= 4) splits *= 2;
+    e.mode = EPI_F32;
+    e.split_stride = static_cast<long long>(M) * N;
+  }
+  gemm_plan(p, a, lda, w, M, N, K, e, h->num_sms, bn, 0, splits);
+}
+
+// workspaces + GEMM plans of the batched pass for `rows` rows and `t_need` text positions per cache slot
+void ensure_batch(wisb_handle* h, int rows, int t_need) {
+  const Dims& dm = h->dims;
+  const int d = dm.d_model, L = dm.n_dec_layers;
+  int Rp = round_up(rows, 128);
+  int tc = round_up(t_need, 32);
+  if (tc > T_MAX) tc = T_MAX;
+  ensure_search(h, rows);
+  if (Rp <= h->bd_rows && tc <= h->bd_tcap) return;
+  if (Rp < h->bd_rows) Rp = h->bd_rows;
+  if (tc < h->bd_tcap) tc = h->bd_tcap;
+  WISB_CUDA(cudaStreamSynchronize(h->stream));
+  drop_graphs(h);
+  const size_t M = static_cast<size_t>(Rp);
+  h->bx.ensure(M * d, true);
+  h->bq.ensure(M * d, true);
+  h->bxn.ensure(M * d, true);    // rows beyond the live ones stay zero: finite GEMM inputs, outputs never stored
+  h->bctx.ensure(M * d, true);
+  h->bh.ensure(M * 4 * d, true);
+  h->bpart.ensure(8 * M * d, true);
+  h->blogits.ensure(M * dm.n_vocab_pad, true);
+  const size_t layer_cache = M * tc * d;
+  h->bkc.release();
+  h->bvc.release();
+  h->bkc.ensure(layer_cache * L, true);
+  h->bvc.ensure(layer_cache * L, true);
+  h->bd_layers.assign(L, BatchLayer());
+  for (int i = 0; i < L; ++i) {
+    const DecLayerW& w = h->dec_w[i];
+    BatchLayer& b = h->bd_layers[i];
+    b.kcache = h->bkc.p + layer_cache * i;
+    b.vcache = h->bvc.p + layer_cache * i;
+    b.ln1g = w.ln1g; b.ln1b = w.ln1b;
+    b.ob = w.ob; b.ln2g = w.ln2g; b.ln2b = w.ln2b;
+    b.cob = w.cob; b.ln3g = w.ln3g; b.ln3b = w.ln3b;
+    b.fc2b = w.fc2b;
+    b.next_g = (i + 1 < L) ? h->dec_w[i + 1].ln1g : h->F("dec.ln.g");
+    b.next_b = (i + 1 < L) ? h->dec_w[i + 1].ln1b : h->F("dec.ln.b");
+    GemmEpi e;
+    e.mode = EPI_DEC_QKV;
+    e.bias = w.qkvb;
+    e.out = h->bq.p;
+    e.ldo = d;
+    e.aux = b.kcache;
+    e.aux2 = b.vcache;
+    e.d_model = d;
+    e.row_slot = h->row_slot.p;
+    e.row_pos = h->row_pos.p;
+    e.t_cap = tc;
+    plan_dec_gemm(h, b.qkv, h->bxn.p, d, w.qkvw, Rp, 3 * d, d, e, false);
+    GemmEpi ep;  // split-K partials; bias / residual / LayerNorm happen in bd_resid_ln_kernel
+    ep.out = h->bpart.p;
+    ep.ldo = d;
+    plan_dec_gemm(h, b.o, h->bctx.p, d, w.ow, Rp, d, d, ep, true);
+    GemmEpi eq;
+    eq.mode = EPI_F32;
+    eq.bias = w.cqb;
+    eq.out = h->bq.p;
+    eq.ldo = d;
+    plan_dec_gemm(h, b.cq, h->bxn.p, d, w.cqw, Rp, d, d, eq, false);
+    plan_dec_gemm(h, b.co, h->bctx.p, d, w.cow, Rp, d, d, ep, true);
+    GemmEpi e1;
+    e1.mode = EPI_F16_GELU;
+    e1.bias = w.fc1b;
+    e1.out = h->bh.p;
+    e1.ldo = 4 * d;
+    plan_dec_gemm(h, b.fc1, h->bxn.p, d, w.fc1w, Rp, 4 * d, d, e1, false);
+    plan_dec_gemm(h, b.fc2, h->bh.p, 4LL * d, w.fc2w, Rp, d, 4 * d, ep, true);
+  }
+  {
+    GemmEpi ev;
+    ev.mode = EPI_F32;
+    ev.out = h->blogits.p;
+    ev.ldo = dm.n_vocab_pad;
+    plan_dec_gemm(h, h->bd_vocab, h->bxn.p, d, h->H("dec.tok_emb"), Rp, dm.n_vocab_pad, d, ev, false);
+  }
+  h->bd_rows = Rp;
+  h->bd_tcap = tc;
+}
+
+BatchArgs make_batch_args(wisb_handle* h, const DecodeCfg& c) {
+  const Dims& dm = h->dims;
+  BatchArgs a;
+  a.d = dm.d_model;
+  a.H = dm.n_heads;
+  a.n_utt = c.n_utt;
+  a.t_cap = h->bd_tcap;
+  a.t_ind = T_MAX;
+  a.pdl = h->batch_pdl;
+  a.tokens = h->tokens.p;
+  a.row_pos = h->row_pos.p;
+  a.row_slot = h->row_slot.p;
+  a.tok_emb = h->H("dec.tok_emb");
+  a.pos_emb = h->F("dec.pos");
+  a.x = h->bx.p;
+  a.xn = h->bxn.p;
+  a.q = h->bq.p;
+  a.ctx = h->bctx.p;
+  a.part = h->bpart.p;
+  a.part_stride = static_cast<long long>(h->bd_rows) * dm.d_model;
+  a.indir0 = h->ind0.p;
+  a.indir1 = h->ind1.p;
+  a.flip = h->flip.p;
+  a.vocab = &h->bd_vocab;
+  return a;
+}
+
+SearchArgs make_batch_search_args(wisb_handle* h, const DecodeCfg& c) {
+  SearchArgs sa = make_search_args(h, c);
+  sa.logits = h->blogits.p;
+  return sa;
+}
+
+void enqueue_batch_step(wisb_handle* h, const DecodeCfg& c) {
+  BatchArgs a = make_batch_args(h, c);
+  a.R = c.n_utt * c.beam;
+  a.rows_per_utt = c.beam;
+  a.with_logits = 1;
+  a.done = h->done.p;
+  h->bd_launches_step = batch_pass_run(a, h->bd_layers.data(), h->dims.n_dec_layers, h->stream) + 4;
+  search_step_run(make_batch_search_args(h, c), h->stream);
+}
+
+// decode utterances [u0, u0 + n_utt) of the encoded batch with ONE shared decoder pass per generated token
+int decode_batch(wisb_handle* h, const DecodeCfg& c, const int32_t* prompts, const int* max_new_host, int32_t* out_ids,
+                 int out_stride, int32_t* out_len, float* out_score) {
+  const Dims& dm = h->dims;
+  cudaStream_t s = h->stream;
+  const int R = c.n_utt * c.beam;
+  const int H = dm.n_heads;
+  ensure_batch(h, R, c.prompt_len + c.max_new);
+  // cross K/V of the utterances of this pass
+  const size_t head_block = static_cast<size_t>(H) * T_ENC_PAD * HEAD_DIM;
+  for (int i = 0; i < dm.n_dec_layers; ++i) {
+    h->bd_layers[i].ck = h->ckv.p + (static_cast<size_t>(i * 2 + 0) * c.B_total + c.u0) * head_block;
+    h->bd_layers[i].cv = h->ckv.p + (static_cast<size_t>(i * 2 + 1) * c.B_total + c.u0) * head_block;
+  }
+  int steps = 0;
+  int* pin = h->pin_i.p + 4;
+  memcpy(pin, prompts + static_cast<size_t>(c.u0) * c.prompt_len, sizeof(int) * c.n_utt * c.prompt_len);
+  WISB_CUDA(cudaMemcpyAsync(h->prompt_dev.p, pin, sizeof(int) * c.n_utt * c.prompt_len, cudaMemcpyHostToDevice, s));
+  int* pin_mx = pin + static_cast<size_t>(c.n_utt) * c.prompt_len;
+  if (c.per_utt_max_new) {
+    memcpy(pin_mx, max_new_host, sizeof(int) * c.n_utt);
+    WISB_CUDA(cudaMemcpyAsync(h->max_new_u.p, pin_mx, sizeof(int) * c.n_utt, cudaMemcpyHostToDevice, s));
+  }
+  if (c.max_new > 0) {
+    // ---- prompt prefix: every utterance's positions [0, prompt_len - 1) as rows of shared passes (<= 8 positions and
+    //      <= the row capacity per pass), K/V into the slot of the utterance's first beam
+    const int pf_len = c.prompt_len - 1;
+    int chunk_max = h->bd_rows / c.n_utt;
+    if (chunk_max > MAX_BEAM) chunk_max = MAX_BEAM;
+    if (chunk_max < 1) chunk_max = 1;
+    for (int p0 = 0; p0 < pf_len; p0 += chunk_max) {
+      const int chunk = pf_len - p0 < chunk_max ? pf_len - p0 : chunk_max;
+      prefill_rows_run(h->tokens.p, h->row_pos.p, h->row_slot.p, h->prompt_dev.p, c.prompt_len, c.n_utt, p0, chunk, c.beam, s);
+      BatchArgs a = make_batch_args(h, c);
+      a.R = c.n_utt * chunk;
+      a.rows_per_utt = chunk;
+      a.prefill = 1;
+      h->launches += 1 + batch_pass_run(a, h->bd_layers.data(), dm.n_dec_layers, s);
+      ++steps;
+    }
+    SearchArgs sa = make_batch_search_args(h, c);
+    search_init_run(sa, h->prompt_dev.p, s, 1);
+    DecGraphs* g = nullptr;
+    if (h->use_graphs) {
+      GraphKey key;
+      memset(&key, 0, sizeof(key));
+      key.n_utt = c.n_utt; key.beam = c.beam; key.prompt_len = c.prompt_len; key.max_new = c.max_new;
+      key.max_hyp = c.max_hyp; key.lp = c.lp; key.u0 = c.u0; key.b_total = c.B_total;
+      key.batched = 1 + c.per_utt_max_new;
+      auto it = h->graphs.find(key);
+      if (it == h->graphs.end()) {
+        if (h->graphs.size() > 64) drop_graphs(h);
+        DecGraphs ng;
+        cudaGraph_t graph;
+        WISB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        enqueue_batch_step(h, c);
+        WISB_CUDA(cudaStreamEndCapture(s, &graph));
+        WISB_CUDA(cudaGraphInstantiate(&ng.step, graph, 0));
+        WISB_CUDA(cudaGraphDestroy(graph));
+        it = h->graphs.emplace(key, ng).first;
+      }
+      g = &it->second;
+    }
+    volatile int* flag = h->pin_i.p;
+    *flag = 0;
+    for (int gs = 0; gs < c.max_new; ++gs) {
+      if (g) WISB_CUDA(cudaGraphLaunch(g->step, s)); else enqueue_batch_step(h, c);
+      ++steps;
+      h->launches += h->bd_launches_step;
+      const bool poll = ((gs + 1) % h->decode_poll == 0) || gs + 1 == c.max_new;
+      if (poll) {
+        WISB_CUDA(cudaMemcpyAsync(const_cast<int*>(flag), &h->st.p->all_done, sizeof(int), cudaMemcpyDeviceToHost, s));
+        WISB_CUDA(cudaStreamSynchronize(s));
+        if (*flag) break;
+      }
+    }
+  }
+  // results
+  int* lens = h->pin_i.p + 4;
+  int* toks = lens + c.n_utt;
+  const int mn = c.max_new > 0 ? c.max_new : 1;
+  WISB_CUDA(cudaMemcpyAsync(lens, h->best_len.p, sizeof(int) * c.n_utt, cudaMemcpyDeviceToHost, s));
+  WISB_CUDA(cudaMemcpyAsync(toks, h->best_tokens.p, sizeof(int) * c.n_utt * mn, cudaMemcpyDeviceToHost, s));
+  WISB_CUDA(cudaMemcpyAsync(h->pin_f.p, h->best_score.p, sizeof(float) * c.n_utt, cudaMemcpyDeviceToHost, s));
+  WISB_CUDA(cudaStreamSynchronize(s));
+  for (int u = 0; u < c.n_utt; ++u) {
+    const int len = c.max_new > 0 ? lens[u] : 0;
+    out_len[c.u0 + u] = len;
+    for (int t = 0; t < len && t < out_stride; ++t) out_ids[static_cast<size_t>(c.u0 + u) * out_stride + t] = toks[u * mn + t];
+    if (out_score) out_score[c.u0 + u] = c.max_new > 0 ? h->pin_f.p[u] : 0.f;
+  }
+  return steps;
+}
+
 template <typename Fn>
 int guarded(wisb_handle* h, Fn&& fn) {
   try {
@@ -992,6 +1262,12 @@ int wisb_set_option(wisb_handle* h, const char* key, int value) {
       h->enc_valid = false;
     }
     else if (k == "mega_trace") h->mega_trace_on = value;
+    else if (k == "batch_rows") {
+      WISB_REQUIRE(value >= 8 && value <= 1024, "batch_rows must be in [8, 1024]");
+      h->batch_rows = value;
+    }
+    else if (k == "batch_pdl") h->batch_pdl = value ? 1 : 0;
+    else if (k == "decoder_batch") h->decoder_batch = value;  // 2 = use the batched pass even for <= 8 rows (tests)
     else throw Error(1, "unknown option '" + k + "'");
   });
 }
@@ -1017,7 +1293,7 @@ int wisb_logmel(wisb_handle* h, const void* pcm, int pcm_dtype, int pcm_on_devic
       if (end > total) total = end;
     }
     cudaStream_t s = h->stream;
-    ensure_encoder(h, B);
+    ensure_mel(h, B);
     h->pcm_off.ensure(B);
     h->pcm_n.ensure(B);
     WISB_CUDA(cudaEventRecord(h->ev[0], s));
@@ -1042,9 +1318,10 @@ int wisb_logmel(wisb_handle* h, const void* pcm, int pcm_dtype, int pcm_on_devic
   });
 }
 
-int wisb_generate(wisb_handle* h, const float* mel, int B, const int32_t* prompts, int prompt_len, int beam_size,
-                  float patience, float length_penalty, int max_length, const int32_t* extra_suppress, int n_extra,
-                  int32_t* out_ids, int out_stride, int32_t* out_len, float* out_score) {
+int wisb_generate_ex(wisb_handle* h, const float* mel, int B, const int32_t* prompts, int prompt_len, int beam_size,
+                     float patience, float length_penalty, int max_length, const int32_t* max_length_per_utt,
+                     const int32_t* extra_suppress, int n_extra, int32_t* out_ids, int out_stride, int32_t* out_len,
+                     float* out_score) {
   return guarded(h, [&] {
     const Dims& dm = h->dims;
     WISB_REQUIRE(h->blob != nullptr, "handle has no model (created by wisb_create_frontend)");
@@ -1057,43 +1334,99 @@ int wisb_generate(wisb_handle* h, const float* mel, int B, const int32_t* prompt
     WISB_REQUIRE(n_extra >= 0 && (n_extra == 0 || extra_suppress != nullptr), "bad extra_suppress");
     for (long long i = 0; i < static_cast<long long>(B) * prompt_len; ++i)
       WISB_REQUIRE(prompts[i] >= 0 && prompts[i] < dm.n_vocab, "prompt token outside the vocabulary");
-    int max_new = max_length / 2 < max_length - prompt_len ? max_length / 2 : max_length - prompt_len;
-    if (max_new < 0) max_new = 0;
+    auto new_tokens = [&](int ml) {  // CTranslate2: at most max_length / 2 new tokens, max_length in total
+      int v = ml / 2 < ml - prompt_len ? ml / 2 : ml - prompt_len;
+      return v < 0 ? 0 : v;
+    };
+    int max_new = new_tokens(max_length);
+    std::vector<int> per_utt;
+    if (max_length_per_utt != nullptr) {
+      per_utt.resize(B);
+      max_new = 0;
+      for (int b = 0; b < B; ++b) {
+        WISB_REQUIRE(max_length_per_utt[b] >= 1 && max_length_per_utt[b] <= dm.n_text_ctx, "per-utterance max_length out of range");
+        per_utt[b] = new_tokens(max_length_per_utt[b]);
+        if (per_utt[b] > max_new) max_new = per_utt[b];
+      }
+    }
     WISB_REQUIRE(out_stride >= max_new, "out_stride smaller than the maximum number of generated tokens");
     cudaStream_t s = h->stream;
     h->launches = 0;
+    for (int i = 1; i <= 5; ++i) h->timing[i] = 0.f;
     WISB_CUDA(cudaEventRecord(h->ev[0], s));
     const bool reuse = upload_mel(h, mel, B);
     set_extra_suppress(h, extra_suppress, n_extra);
     WISB_CUDA(cudaEventRecord(h->ev[2], s));
-    encode_for_decode(h, B, reuse);
-    WISB_CUDA(cudaEventRecord(h->ev[4], s));
-    const int per_pass = DEC_MAX_ROWS / beam_size;
-    int steps = 0;
-    for (int u0 = 0; u0 < B; u0 += per_pass) {
-      DecodeCfg c;
-      c.u0 = u0;
-      c.n_utt = (B - u0 < per_pass) ? B - u0 : per_pass;
-      c.B_total = B;
-      c.beam = beam_size;
-      c.prompt_len = prompt_len;
-      c.max_new = max_new;
-      c.max_hyp = static_cast<int>(beam_size * patience + 0.5f);
-      if (c.max_hyp < 1) c.max_hyp = 1;
-      c.lp = length_penalty;
-      steps += decode_pass(h, c, prompts, out_ids, out_stride, out_len, out_score);
-    }
-    WISB_CUDA(cudaEventRecord(h->ev[5], s));
-    WISB_CUDA(cudaStreamSynchronize(s));
+    WISB_CUDA(cudaEventSynchronize(h->ev[2]));
     WISB_CUDA(cudaEventElapsedTime(&h->timing[1], h->ev[0], h->ev[2]));
-    WISB_CUDA(cudaEventElapsedTime(&h->timing[2], h->ev[2], h->ev[3]));
-    WISB_CUDA(cudaEventElapsedTime(&h->timing[3], h->ev[3], h->ev[4]));
-    WISB_CUDA(cudaEventElapsedTime(&h->timing[4], h->ev[4], h->ev[5]));
+    DecodeCfg c;
+    c.beam = beam_size;
+    c.prompt_len = prompt_len;
+    c.max_hyp = static_cast<int>(beam_size * patience + 0.5f);
+    if (c.max_hyp < 1) c.max_hyp = 1;
+    c.lp = length_penalty;
+    // Utterances are encoded and decoded in groups that share every decoder pass: the group's rows (utterances x beams)
+    // are the M dimension of the batched pass, so the decoder weights stream once per generated token for the whole
+    // group.  The group size only bounds the workspaces (cross K/V: 252 MB per large-v2 utterance).
+    const bool mega = B * beam_size <= DEC_MAX_ROWS && h->decoder_batch != 2;
+    int group = mega ? B : h->batch_rows / beam_size;
+    if (group < 1) group = 1;
+    int steps = 0;
+    for (int g0 = 0; g0 < B; g0 += group) {
+      const int n = B - g0 < group ? B - g0 : group;
+      WISB_CUDA(cudaEventRecord(h->ev[2], s));
+      if (reuse) {
+        WISB_CUDA(cudaEventRecord(h->ev[3], s));
+      } else {
+        run_encoder(h, n, -1, true, g0);
+        h->enc_valid = h->encoder_cache != 0 && h->mel_cache_B == B && n == B;
+      }
+      WISB_CUDA(cudaEventRecord(h->ev[4], s));
+      c.u0 = 0;
+      c.n_utt = n;
+      c.B_total = n;
+      c.max_new = max_new;
+      c.per_utt_max_new = 0;
+      if (!per_utt.empty()) {
+        c.per_utt_max_new = 1;
+        c.max_new = 0;
+        for (int u = 0; u < n; ++u) c.max_new = per_utt[g0 + u] > c.max_new ? per_utt[g0 + u] : c.max_new;
+      }
+      const int32_t* gp = prompts + static_cast<size_t>(g0) * prompt_len;
+      int32_t* gi = out_ids + static_cast<size_t>(g0) * out_stride;
+      if (mega) {
+        WISB_REQUIRE(per_utt.empty() || c.max_new == max_new, "internal: per-utterance limits on the small path");
+        if (!per_utt.empty()) {  // small path: the search kernels read the per-utterance caps from the same buffer
+          WISB_CUDA(cudaMemcpyAsync(h->max_new_u.p, per_utt.data() + g0, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+          WISB_CUDA(cudaStreamSynchronize(s));
+        }
+        steps += decode_pass(h, c, gp, gi, out_stride, out_len + g0, out_score ? out_score + g0 : nullptr);
+      } else {
+        steps += decode_batch(h, c, gp, per_utt.empty() ? nullptr : per_utt.data() + g0, gi, out_stride, out_len + g0,
+                              out_score ? out_score + g0 : nullptr);
+      }
+      WISB_CUDA(cudaEventRecord(h->ev[5], s));
+      WISB_CUDA(cudaStreamSynchronize(s));
+      float t;
+      WISB_CUDA(cudaEventElapsedTime(&t, h->ev[2], h->ev[3]));
+      h->timing[2] += t;
+      WISB_CUDA(cudaEventElapsedTime(&t, h->ev[3], h->ev[4]));
+      h->timing[3] += t;
+      WISB_CUDA(cudaEventElapsedTime(&t, h->ev[4], h->ev[5]));
+      h->timing[4] += t;
+    }
     WISB_CUDA(cudaEventElapsedTime(&h->timing[5], h->ev[0], h->ev[5]));
     h->timing[6] = static_cast<float>(steps);
     h->timing[7] = static_cast<float>(h->launches);
     h->prof_collect();
   });
+}
+
+int wisb_generate(wisb_handle* h, const float* mel, int B, const int32_t* prompts, int prompt_len, int beam_size,
+                  float patience, float length_penalty, int max_length, const int32_t* extra_suppress, int n_extra,
+                  int32_t* out_ids, int out_stride, int32_t* out_len, float* out_score) {
+  return wisb_generate_ex(h, mel, B, prompts, prompt_len, beam_size, patience, length_penalty, max_length, nullptr,
+                          extra_suppress, n_extra, out_ids, out_stride, out_len, out_score);
 }
 
 int wisb_detect_language(wisb_handle* h, const float* mel, int B, int32_t* lang_ids_out, float* probs_out) {
@@ -1207,6 +1540,26 @@ int wisb_debug_forced_logits(wisb_handle* h, const float* mel, const int32_t* to
     c.u0 = 0; c.n_utt = 1; c.B_total = 1; c.beam = 1; c.prompt_len = n_tokens; c.max_new = 1; c.max_hyp = 1; c.lp = 1.f;
     memcpy(h->pin_i.p + 4, tokens, sizeof(int) * n_tokens);
     WISB_CUDA(cudaMemcpyAsync(h->prompt_dev.p, h->pin_i.p + 4, sizeof(int) * n_tokens, cudaMemcpyHostToDevice, s));
+    if (h->decoder_batch == 2) {  // the batched pass, one row: position p of the token list per pass
+      ensure_batch(h, 1, n_tokens);
+      const size_t head_block = static_cast<size_t>(dm.n_heads) * T_ENC_PAD * HEAD_DIM;
+      for (int i = 0; i < dm.n_dec_layers; ++i) {
+        h->bd_layers[i].ck = h->ckv.p + static_cast<size_t>(i * 2 + 0) * head_block;
+        h->bd_layers[i].cv = h->ckv.p + static_cast<size_t>(i * 2 + 1) * head_block;
+      }
+      for (int p = 0; p < n_tokens; ++p) {
+        prefill_rows_run(h->tokens.p, h->row_pos.p, h->row_slot.p, h->prompt_dev.p, n_tokens, 1, p, 1, 1, s);
+        BatchArgs a = make_batch_args(h, c);
+        a.R = 1;
+        a.rows_per_utt = 1;
+        a.prefill = 1;
+        a.with_logits = 1;
+        batch_pass_run(a, h->bd_layers.data(), dm.n_dec_layers, s);
+        WISB_CUDA(cudaMemcpyAsync(logits_out + static_cast<size_t>(p) * dm.n_vocab, h->blogits.p, sizeof(float) * dm.n_vocab, cudaMemcpyDeviceToHost, s));
+      }
+      WISB_CUDA(cudaStreamSynchronize(s));
+      return;
+    }
     search_init_run(make_search_args(h, c), h->prompt_dev.p, s);
     if (h->decoder_mega) upload_mega_layers(h, c);
     for (int p = 0; p < n_tokens; ++p) {

@@ -26,9 +26,9 @@ constexpr int GEMM_THREADS = 192;
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 160 ? 5 : 6);
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 160 ? 5 : (BN == 128 ? 6 : 8));
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
-  static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;  // power of two >= two accumulator buffers
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);  // power of two >= two accumulator buffers
   static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -50,7 +50,7 @@ __device__ __forceinline__ void store_f16x32(__half* dst, const float (&f)[32]) 
 }
 
 // One thread owns one output row and 32 consecutive columns [col0, col0+32).
-__device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, int row, int col0, const uint32_t (&v)[32]) {
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, int row, int col0, const uint32_t (&v)[32], int split) {
   float f[32];
   if (e.bias != nullptr) {
     const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
@@ -113,7 +113,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, int row, int co
       const int c = within - kv * e.d_model;
       const int head = c >> 6, e0 = c & 63;
       const int b = row / T_ENC_PAD, t = row - b * T_ENC_PAD;
-      long long idx = ((((static_cast<long long>(layer) * 2 + kv) * e.batch + b) * e.n_heads + head) * T_ENC_PAD + t) * 64 + e0;
+      long long idx = ((((static_cast<long long>(layer) * 2 + kv) * e.batch + e.batch_off + b) * e.n_heads + head) * T_ENC_PAD + t) * 64 + e0;
       store_f16x32(reinterpret_cast<__half*>(e.out) + idx, f);
       break;
     }
@@ -132,9 +132,24 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, int row, int co
       break;
     }
     case EPI_F32: {
-      float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + static_cast<long long>(row) * e.ldo + col0);
+      float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + split * e.split_stride +
+                                             static_cast<long long>(row) * e.ldo + col0);
 #pragma unroll
       for (int i = 0; i < 8; ++i) o4[i] = make_float4(f[4 * i + 0], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+      break;
+    }
+    case EPI_DEC_QKV: {
+      const int d = e.d_model;
+      if (col0 < d) {  // query: fp32 [rows, d]
+        float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + static_cast<long long>(row) * e.ldo + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o4[i] = make_float4(f[4 * i + 0], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+      } else {         // key / value of this row's position, straight into the self-attention cache
+        const bool is_v = col0 >= 2 * d;
+        const int c = col0 - (is_v ? 2 * d : d);
+        const long long at = (static_cast<long long>(__ldg(e.row_slot + row)) * e.t_cap + __ldg(e.row_pos + row)) * d + c;
+        store_f16x32(reinterpret_cast<__half*>(is_v ? e.aux2 : e.aux) + at, f);
+      }
       break;
     }
     default:
@@ -148,7 +163,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, int row, int co
 template <int BN, bool kMC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N, int K,
-               int a_wrap, const GemmEpi epi) {
+               int a_wrap, int k_splits, const GemmEpi epi) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -167,17 +182,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = M / BM;
+  pdl_launch_dependents();  // (no-op unless the next kernel was launched with the programmatic-serialization attribute)
   const int n_tiles = (N + BN - 1) / BN;
-  const int k_blocks = K / BK;
+  // split-K: a work item is (tile, K range); its partial goes to its own output slab (EPI_F32) and is summed by the
+  // consumer kernel in a fixed order (deterministic, no atomics)
+  const int k_blocks = K / BK / k_splits;
   // work items: single tiles, or (kMC) vertical tile pairs handled by a 2-CTA cluster (rank r takes M tile 2 * pair + r)
   const uint32_t crank = kMC ? cluster_ctarank() : 0u;
-  const int m_units = kMC ? m_tiles / 2 : m_tiles;
-  const int total_tiles = m_units * n_tiles;
   const int first_unit = kMC ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int unit_stride = kMC ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  auto unit_m0 = [&](int unit) { return ((unit % m_units) * (kMC ? 2 : 1) + static_cast<int>(crank)) * BM; };
-  auto unit_n0 = [&](int unit) { return (unit / m_units) * BN; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -201,6 +214,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (kMC) cluster_sync_all();  // peer barriers are initialised before any multicast copy / remote commit can arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its results are visible from here on
+  // rows actually present (device-side count, e.g. the rows of the utterances still decoding): whole M tiles beyond it
+  // are skipped by all three roles alike
+  int m_tiles = M / BM;
+  if (epi.m_dyn != nullptr) {
+    const int mt = (*epi.m_dyn + BM - 1) / BM;
+    if (mt < m_tiles) m_tiles = mt;
+  }
+  if (kMC) m_tiles = (m_tiles + 1) & ~1;  // pairs of M tiles (the tensor map always covers an even number of tiles here)
+  const int m_units = kMC ? m_tiles / 2 : m_tiles;
+  const int total_tiles = m_units * n_tiles * k_splits;
+  auto unit_split = [&](int unit) { return unit % k_splits; };
+  auto unit_m0 = [&](int unit) { return (((unit / k_splits) % m_units) * (kMC ? 2 : 1) + static_cast<int>(crank)) * BM; };
+  auto unit_n0 = [&](int unit) { return ((unit / k_splits) / m_units) * BN; };
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -210,7 +237,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int tile = first_unit; tile < total_tiles; tile += unit_stride) {
         const int m0 = unit_m0(tile);
         const int n0 = unit_n0(tile);
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        const int kb0 = unit_split(tile) * k_blocks;
+        for (int kbl = 0; kbl < k_blocks; ++kbl) {
+          const int kb = kb0 + kbl;
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
           // a_wrap > 0: logical A row r = [phys row r | first K - a_wrap columns of phys row r + 1]  (conv2 view)
@@ -275,6 +304,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t aphase = (it >> 1) & 1u;
       const int m0 = unit_m0(tile);
       const int n0 = unit_n0(tile);
+      const int split = unit_split(tile);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
@@ -286,7 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c * 32), v);
         tmem_ld_wait();
-        if (row < epi.m_valid) epilogue_chunk(epi, row, col0, v);
+        if (row < epi.m_valid) epilogue_chunk(epi, row, col0, v, split);
       }
       tc_fence_before();
       __syncwarp();
@@ -345,15 +375,18 @@ void make_tmap_f16_2d(CUtensorMap* map, const void* ptr, long long cols, long lo
 }
 
 void gemm_plan(GemmPlan& p, const __half* a, long long lda, const __half* w, int M, int N, int K, const GemmEpi& epi,
-               int num_sms, int force_bn, int a_wrap) {
+               int num_sms, int force_bn, int a_wrap, int k_splits) {
   WISB_REQUIRE(M > 0 && M % BM == 0, "gemm: M must be a positive multiple of 128");
   WISB_REQUIRE(K > 0 && K % BK == 0, "gemm: K must be a positive multiple of 64");
   WISB_REQUIRE(N > 0 && N % 32 == 0, "gemm: N must be a positive multiple of 32");
   WISB_REQUIRE((lda * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
                "gemm: operands must be 16-byte aligned");
+  WISB_REQUIRE(k_splits >= 1 && (K / BK) % k_splits == 0, "gemm: K blocks must divide evenly over the K splits");
+  WISB_REQUIRE(k_splits == 1 || (epi.mode == EPI_F32 && epi.split_stride > 0), "gemm: split-K needs the EPI_F32 partial epilogue");
   p.M = M;
   p.N = N;
   p.K = K;
+  p.k_splits = k_splits;
   p.epi = epi;
   if (p.epi.m_valid <= 0) p.epi.m_valid = M;
   if (p.epi.n_valid <= 0) p.epi.n_valid = N;
@@ -374,9 +407,9 @@ void gemm_plan(GemmPlan& p, const __half* a, long long lda, const __half* w, int
     }
     if (bn == 0) bn = 128;
   }
-  WISB_REQUIRE(bn == 128 || bn == 160 || bn == 256, "gemm: BN must be 128, 160 or 256");
+  WISB_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "gemm: BN must be 64, 128, 160 or 256");
   p.BN = bn;
-  const int tiles = (M / BM) * ((N + bn - 1) / bn);
+  const int tiles = (M / BM) * ((N + bn - 1) / bn) * k_splits;
   // 2-CTA clusters with multicast W tiles whenever the M tiles pair up and N tiles are whole
   p.mcast = (!no_mcast && (M / BM) % 2 == 0 && N % bn == 0 && a_wrap == 0 && num_sms >= 2) ? 1 : 0;
   if (p.mcast) {
@@ -406,18 +439,22 @@ void gemm_launch(const GemmPlan& p, cudaStream_t stream) {
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = GemmCfg<BN>::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kMC ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  WISB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, kMC>, p.map_a, p.map_b, p.M, p.N, p.K, p.a_wrap, p.epi));
+  cfg.numAttrs = p.pdl ? 2 : 1;
+  WISB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, kMC>, p.map_a, p.map_b, p.M, p.N, p.K, p.a_wrap, p.k_splits, p.epi));
 }
 
 void gemm_run(const GemmPlan& p, cudaStream_t stream) {
-  if (p.BN == 256) {
+  if (p.BN == 64) {
+    if (p.mcast) gemm_launch<64, true>(p, stream); else gemm_launch<64, false>(p, stream);
+  } else if (p.BN == 256) {
     if (p.mcast) gemm_launch<256, true>(p, stream); else gemm_launch<256, false>(p, stream);
   } else if (p.BN == 160) {
     if (p.mcast) gemm_launch<160, true>(p, stream); else gemm_launch<160, false>(p, stream);

@@ -14,6 +14,8 @@ enum EpiMode : int {
   EPI_CROSSKV = 4,    // out16 scattered to [layer][k|v][b][head][1536][64]
   EPI_F32 = 5,        // out32 = acc (+ bias)
   EPI_QKV_VT = 6,     // cols < 2d: out16 = acc + bias; cols >= 2d (V): aux16[b][head][e][t] = acc + bias (transposed)
+  EPI_DEC_QKV = 7,    // batched decoder pass: cols < d: out32 (q) = acc + bias; K / V columns go to the self-attention
+                      // cache rows [(row_slot[row] * t_cap + row_pos[row]) * d + e] of aux (K) / aux2 (V) as fp16
 };
 
 struct GemmEpi {
@@ -24,20 +26,27 @@ struct GemmEpi {
   int m_valid = 0;     // rows >= m_valid are not written
   int n_valid = 0;     // cols >= n_valid are not written (multiple of 32)
   const float* pos = nullptr;  // EPI_CONV2: [1500, N] float32
-  void* aux = nullptr;         // EPI_QKV_VT: Vt buffer
+  void* aux = nullptr;         // EPI_QKV_VT: Vt buffer; EPI_DEC_QKV: K cache of the layer
+  void* aux2 = nullptr;        // EPI_DEC_QKV: V cache of the layer
   int d_model = 0, n_heads = 0, batch = 0;  // EPI_CROSSKV / EPI_QKV_VT
+  int batch_off = 0;           // EPI_CROSSKV: window b of this call is utterance batch_off + b of the `batch`-wide K/V buffer
+  const int* row_slot = nullptr;  // EPI_DEC_QKV: cache slot / position of every row (device arrays)
+  const int* row_pos = nullptr;
+  int t_cap = 0;               // EPI_DEC_QKV: positions per cache slot
+  long long split_stride = 0;  // split-K (EPI_F32 only): partial of split s goes to out + s * split_stride elements
+  const int* m_dyn = nullptr;  // optional device-side row count: M tiles at or beyond it are skipped
 };
 
 struct GemmPlan {
   CUtensorMap map_a, map_b;
-  int M = 0, N = 0, K = 0, BN = 128, grid = 0, a_wrap = 0, mcast = 0;
+  int M = 0, N = 0, K = 0, BN = 128, grid = 0, a_wrap = 0, mcast = 0, k_splits = 1, pdl = 0;
   GemmEpi epi;
 };
 
 // A: M rows of K fp16, row r starts at a + r * lda (lda in elements; may be < K for the overlapping-row view conv2 uses)
 // a_wrap > 0 (conv2): A is stored as rows of `a_wrap` (= lda) elements and logical row r continues into row r + 1.
 void gemm_plan(GemmPlan& p, const __half* a, long long lda, const __half* w, int M, int N, int K, const GemmEpi& epi,
-               int num_sms, int force_bn = 0, int a_wrap = 0);
+               int num_sms, int force_bn = 0, int a_wrap = 0, int k_splits = 1);
 // (force_bn < 0: same |force_bn| tile but without the 2-CTA multicast clusters -- diagnostics)
 void gemm_run(const GemmPlan& p, cudaStream_t stream);
 // slow SIMT cross-check used only by the diagnostics entry point / tests

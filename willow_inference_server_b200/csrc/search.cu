@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(32) search_bookkeeping_kernel(const SearchArgs
   }
   const float* cs = a.cand_score + u * MAX_CAND;
   const int* ci = a.cand_idx + u * MAX_CAND;
-  const bool is_last = (gen + 1 == a.max_new);
+  const bool is_last = (gen + 1 >= (a.max_new_u != nullptr ? a.max_new_u[u] : a.max_new));
   const float norm = (a.length_penalty != 0.f) ? powf(static_cast<float>(gen + 1), a.length_penalty) : 1.f;
   if (lane == 0) {
     int n_hyp = a.n_hyp[u];
@@ -276,9 +276,23 @@ __global__ void __launch_bounds__(32) search_bookkeeping_kernel(const SearchArgs
 }
 
 __global__ void search_advance_kernel(const SearchArgs a) {
-  a.st->pos += 1;
-  a.st->gen_step += 1;
-  *a.flip ^= 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    a.st->pos += 1;
+    a.st->gen_step += 1;
+    *a.flip ^= 1;
+  }
+  if (a.row_pos != nullptr && i < a.n_utt * a.beam) a.row_pos[i] += 1;
+}
+
+__global__ void prefill_rows_kernel(int* tokens, int* row_pos, int* row_slot, const int* prompt, int prompt_len, int rows,
+                                    int p0, int chunk, int beam) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const int u = i / chunk, p = p0 + i % chunk;
+  tokens[i] = prompt[u * prompt_len + p];
+  row_pos[i] = p;
+  row_slot[i] = u * beam;
 }
 
 __global__ void prefill_advance_kernel(int* tokens, const int* prompt, int prompt_len, int R, int beam, DecState* st) {
@@ -304,6 +318,10 @@ __global__ void search_init_kernel(const SearchArgs a, const int* prompt, int sh
   for (int i = tid; i < R; i += n) {
     a.tokens[i] = prompt[(i / a.beam) * a.prompt_len + (shared_prefix ? a.prompt_len - 1 : 0)];
     a.cum[i] = 0.f;
+    if (a.row_pos != nullptr) {
+      a.row_pos[i] = shared_prefix ? a.prompt_len - 1 : 0;
+      a.row_slot[i] = i;
+    }
   }
   for (int i = tid; i < a.n_utt; i += n) {
     a.done[i] = 0;
@@ -346,7 +364,14 @@ void search_step_run(const SearchArgs& a, cudaStream_t stream) {
   topk_partial_kernel<<<dim3(TOPK_CHUNKS, R), TK_THREADS, 0, stream>>>(a);
   topk_merge_kernel<<<a.n_utt, TK_THREADS, 0, stream>>>(a);
   search_bookkeeping_kernel<<<a.n_utt, 32, 0, stream>>>(a);
-  search_advance_kernel<<<1, 1, 0, stream>>>(a);
+  search_advance_kernel<<<cdiv(R, 256), 256, 0, stream>>>(a);
+  WISB_CUDA(cudaGetLastError());
+}
+
+void prefill_rows_run(int* tokens, int* row_pos, int* row_slot, const int* prompt, int prompt_len, int n_utt, int p0,
+                      int chunk, int beam, cudaStream_t stream) {
+  const int rows = n_utt * chunk;
+  prefill_rows_kernel<<<cdiv(rows, 256), 256, 0, stream>>>(tokens, row_pos, row_slot, prompt, prompt_len, rows, p0, chunk, beam);
   WISB_CUDA(cudaGetLastError());
 }
 

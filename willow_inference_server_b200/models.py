@@ -175,9 +175,15 @@ class Whisper:
         extra = [int(t) for t in suppress_tokens if t >= 0]
         p = np.asarray(prompts, np.int32)
         parts = self._split(n, mel)
+        # extension over CTranslate2: `max_length` may be one int per window (requests with different limits coalesced
+        # into one call by batcher.TranscribeBatcher); a plain int is the CTranslate2 meaning
+        ml = None if np.isscalar(max_length) else np.asarray(max_length, np.int32)
+        if ml is not None and ml.shape != (n,):
+            raise ValueError("max_length must be an int or one int per feature window")
 
         def job(i, s, e):
-            return lambda: self._handles[i].generate(mel[s:e], p[s:e], beam_size, patience, length_penalty, max_length, extra)
+            return lambda: self._handles[i].generate(mel[s:e], p[s:e], beam_size, patience, length_penalty,
+                                                     max_length if ml is None else ml[s:e], extra)
 
         outs = self._run([job(*pt) for pt in parts])
         results = []

@@ -199,7 +199,7 @@ def pack_state_dict(sd: dict, dims: WhisperDims) -> dict:
 # seeded synthetic weights (there are no real checkpoints in this image)
 # ---------------------------------------------------------------------------
 def synth_state_dict(dims: WhisperDims, seed: int = 0, logit_std: float = 4.0, qk_gain: float = 2.5,
-                     resid_std: float = 8.0, eot_ramp: tuple | None = None) -> dict:
+                     resid_std: float = 8.0, eot_ramp: tuple | None = None, script: tuple | None = None) -> dict:
     """Deterministic random Whisper weights under HF names.
 
     Every GEMM weight is rounded to float16 so oracle (fp32 math) and engine
@@ -208,6 +208,16 @@ def synth_state_dict(dims: WhisperDims, seed: int = 0, logit_std: float = 4.0, q
     the decoder positional table so that hypotheses terminate at data-dependent
     steps (exercises the beam-search finish rules); ``None`` means EOT is
     essentially never the arg-max and decoding runs to ``max_length``.
+
+    ``script=(n_alt, rho, off)`` makes the output distribution PEAKED the way a trained model's is
+    ("peaked-logit scaling so argmax margins >> rounding noise"): every text
+    position gets ``n_alt`` seeded "plausible next tokens" whose logits are lifted through the decoder
+    positional table to ``(off + k) * rho`` times the standard deviation of the Gaussian (audio / history
+    dependent) part of the logits, k = n_alt-1 .. 0 -- far above the bulk of the vocabulary (the maximum of
+    51865 Gaussian draws is ~4.3 of those deviations).  Which alternative wins still depends on the audio, but
+    candidates are separated by O(rho) deviations instead of the ~0.01-wide near-ties of a flat random model,
+    so greedy / beam transcripts are robust to fp16-vs-fp32 rounding.  The share of the residual stream the
+    script takes is solved from ``rho`` and d_model, so the same setting works at every model size.
     """
     dims.validate()
     d = dims.d_model
@@ -304,6 +314,30 @@ def synth_state_dict(dims: WhisperDims, seed: int = 0, logit_std: float = 4.0, q
     with ThreadPoolExecutor(max_workers=max(1, min(32, (_os.cpu_count() or 1)))) as ex:
         for k, a in zip(names, ex.map(lambda k: sd[k].fn(), names)):
             sd[k] = a
+    if script is not None:
+        n_alt, rho, off = script
+        emb = sd[dd + "embed_tokens.weight"]
+        mult = np.asarray([off + (int(n_alt) - 1 - j) for j in range(int(n_alt))], np.float64)
+        # xn = LN(x) has |xn|^2 = d; a share `frac` of it goes to the scripted directions, the rest (the "noise") keeps
+        # the audio / history dependence:  boost_j = c_j * logit_std with c_j = c0 * mult_j, noise = sqrt(1 - frac) *
+        # logit_std, c0 = rho * sqrt(1 - frac), sum_j c_j^2 = d * frac
+        kk = float((mult ** 2).sum()) * rho * rho
+        frac = kk / (d + kk)
+        c = rho * np.sqrt(1.0 - frac) * mult
+        s_eff = resid_std / np.sqrt(1.0 - frac)  # residual-stream std once the scripted components are in it
+        banned = set(dims.suppress_ids) | set(dims.suppress_ids_begin)
+        rng = np.random.default_rng(np.random.SeedSequence(entropy=ss.entropy, spawn_key=(10 ** 6,)))
+        pos = sd[dd + "embed_positions.weight"].astype(np.float64)
+        for p in range(dims.n_text_ctx):
+            alts = []
+            while len(alts) < int(n_alt):
+                t = int(rng.integers(300, dims.eot))  # ordinary text tokens only
+                if t not in banned and t not in alts:
+                    alts.append(t)
+            for j, t in enumerate(alts):
+                nrm = np.linalg.norm(emb[t])
+                pos[p] += (c[j] * s_eff * logit_std / (nrm * nrm)) * emb[t].astype(np.float64)
+        sd[dd + "embed_positions.weight"] = pos.astype(np.float32)
     if eot_ramp is not None:
         p0, slope = eot_ramp
         emb = sd[dd + "embed_tokens.weight"]
