@@ -142,3 +142,28 @@ def test_random_streams_roundtrip(seed):
                 row.append({"kind": "verbatim"})
         specs.append(row)
     _roundtrip(x, bps=bps, blocks=blocks, stereo_modes=modes, specs=specs, md5=bool(seed % 2))
+
+
+@pytest.mark.parametrize("bps", [8, 12, 16, 20, 24])
+def test_load_audio_amplitude_for_every_sample_width(bps):
+    # full scale is 2^(bps-1) whatever the width (what soundfile / librosa.load hand do_whisper, main.py:579): the log-mel
+    # front end is not gain invariant, so a 24-bit stream decoded 48 dB too quiet would silently change every feature
+    n = 3000
+    x = _signal(n, 1, bps, 11)[:, 0]
+    data = fw.encode(x, bps=bps, blocks=[n])
+    got = audio.load_audio(data)
+    want = (x.astype(np.float64) / float(1 << (bps - 1))).astype(np.float32)
+    assert got.dtype == np.float32 and got.shape == (n,)
+    assert np.array_equal(got, want)
+    assert 0.35 < np.abs(got).max() < 0.5
+
+
+def test_streaminfo_sample_count_is_not_trusted():
+    # a 42-byte "file" whose STREAMINFO claims 2^36 - 1 samples must be rejected before anything is allocated
+    x = _signal(64, 1, 16, 3)[:, 0]
+    data = bytearray(fw.encode(x, blocks=[64]))
+    # STREAMINFO body starts at byte 8; total samples = low 36 bits of bytes 13..17 of the body
+    data[8 + 13] |= 0x0F
+    data[8 + 14 : 8 + 18] = b"\xff\xff\xff\xff"
+    with pytest.raises(ValueError):
+        _lib.flac_decode(bytes(data[:42]))

@@ -67,15 +67,22 @@ def test_batch16_equals_single_and_oracle(pair, beam):
 def test_per_utterance_max_length_in_one_pass(pair):
     dims, oracle, h = pair
     mel = mel_inputs(6)
-    limits = [16, 30, 448, 12, 24, 40]
+    limits = [16, 30, 60, 12, 24, 40]
     got, _ = h.generate(mel, [PROMPT] * 6, beam_size=5, max_length=np.asarray(limits, np.int32), extra_suppress=[dims.eot])
-    for i, ml in enumerate(limits):
-        want, _ = h.generate(mel[i : i + 1], [PROMPT], beam_size=5, max_length=ml, extra_suppress=[dims.eot])
-        assert got[i] == want[0], i
-        assert len(got[i]) == min(ml // 2, ml - 4)
+    h.set_option("decoder_batch", 2)  # the separate calls take the batched pass too: same arithmetic, row for row
+    try:
+        for i, ml in enumerate(limits):
+            want, _ = h.generate(mel[i : i + 1], [PROMPT], beam_size=5, max_length=ml, extra_suppress=[dims.eot])
+            assert got[i] == want[0], i
+            assert len(got[i]) == min(ml // 2, ml - 4)
+    finally:
+        h.set_option("decoder_batch", 1)
     res, robust = robust_cases(oracle, mel[:2], [PROMPT] * 2, 5, max_length=16, suppress_tokens=(-1, dims.eot))
     if 0 in robust:
         assert got[0] == res[0].sequences_ids[0]
+    res, robust = robust_cases(oracle, mel[3:4], [PROMPT], 5, max_length=12, suppress_tokens=(-1, dims.eot))
+    if robust:
+        assert got[3] == res[0].sequences_ids[0]
     with pytest.raises(ValueError):
         h.generate(mel, [PROMPT] * 6, beam_size=5, max_length=np.asarray([16, 30], np.int32))
 

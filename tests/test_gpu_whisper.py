@@ -158,7 +158,7 @@ def test_argument_errors(pair):
 def test_wider_model_batch(pair):
     # d=256, 4 heads, 3 layers: exercises multi-head indexing, BN=256 tiles and a 7-utterance batch (35 rows: the
     # batched decoder pass)
-    dims, oracle, h = model_pair(256, 4, 3, 5)
+    dims, oracle, h = model_pair(256, 4, 3, 7)
     mel = np.concatenate([mel_inputs(6)[:4], mel_inputs(6)[:3]])
     want = oracle.encode(mel[:2]).numpy()
     assert np.abs(h.debug_encode(mel[:2]) - want).max() <= ENC_TOL

@@ -233,6 +233,11 @@ def flac_decode(data: bytes):
     md5 = (C.c_uint8 * 16)()
     if l.wisb_flac_info(buf.ctypes.data, buf.size, C.byref(sr), C.byref(ch), C.byref(bps), C.byref(n), md5):
         raise ValueError("FLAC: " + l.wisb_flac_last_error().decode())
+    # STREAMINFO is untrusted input: a frame is >= 9 bytes and carries <= 65535 samples per channel, so the stream
+    # cannot hold more inter-channel samples than that, whatever the header claims (and 2^30 samples is the hard cap)
+    bound = (buf.size // 9 + 1) * 65535
+    if n.value < 0 or n.value > bound or n.value * max(ch.value, 1) > (1 << 30):
+        raise ValueError(f"FLAC: STREAMINFO announces {n.value} samples, impossible for a {buf.size}-byte stream")
     out = np.zeros((n.value, ch.value), np.int32)
     got = C.c_int64()
     if l.wisb_flac_decode(buf.ctypes.data, buf.size, out.ctypes.data, n.value, C.byref(got)):

@@ -157,7 +157,15 @@ def transcribe_long(model, audio, prompt, tokenizer, *, beam_size: int = 5, batc
     Returns the merged token ids (numpy int array), ready for ``whisper_processor.decode``."""
     from .models import StorageView
 
-    mel, strides = log_mel_chunks(audio)
+    pcm = np.asarray(audio)
+    if pcm.ndim == 1 and pcm.shape[0] <= N_SAMPLES:
+        # <= 30 s: the reference does not window at all (main.py:587-617), it decodes one zero-padded 30-s window
+        if pcm.dtype not in (np.float32, np.int16):
+            pcm = pcm.astype(np.float32)
+        mel = _get_frontend().logmel(np.ascontiguousarray(pcm), [0], [pcm.shape[0]])
+        strides = [(pcm.shape[0], 0, 0)]
+    else:
+        mel, strides = log_mel_chunks(audio)
     if not strides:
         return np.zeros(0, np.int64)
     seqs = []
@@ -195,8 +203,8 @@ def find_longest_common_sequence(sequences, tokenizer):
     return np.array(merged)
 
 
-def decode_flac(src, verify: bool = True):
-    """FLAC file path / bytes -> (pcm, sample_rate).  pcm: int16 (<= 16 bits per sample) or int32, shape [n] for mono,
+def decode_flac(src, verify: bool = True, return_bps: bool = False):
+    """FLAC file path / bytes -> (pcm, sample_rate[, bits_per_sample]).  pcm: int16 (<= 16 bits per sample) or int32, shape [n] for mono,
     [n, channels] otherwise.  The decode half of ``librosa.load`` (/root/reference/main.py:579) for the FLAC inputs WIS
     is tested with; with ``verify`` the decoded PCM is checked against the MD5 the encoder stored in STREAMINFO (an
     all-zero signature means "not set" and is skipped).  Host code in libwisb200 (csrc/flac.cu); no GPU involved."""
@@ -210,15 +218,17 @@ def decode_flac(src, verify: bool = True):
         if hashlib.md5(raw).digest() != md5:
             raise ValueError("FLAC: decoded audio does not match the MD5 signature in STREAMINFO")
     out = pcm.astype(np.int16) if bps <= 16 else pcm
-    return (out[:, 0] if out.shape[1] == 1 else out), sr
+    out = out[:, 0] if out.shape[1] == 1 else out
+    return (out, sr, bps) if return_bps else (out, sr)
 
 
 def load_audio(src, sr: int = SAMPLE_RATE) -> np.ndarray:
     """FLAC -> float32 mono in [-1, 1) at 16 kHz, as ``librosa.load(file, sr=16000)`` returns it for inputs that are
     already sampled at 16 kHz (the reference's fixtures are).  Other rates raise: resampling stays with the caller."""
-    pcm, rate = decode_flac(src)
+    pcm, rate, bps = decode_flac(src, return_bps=True)
     if rate != sr:
         raise ValueError(f"{rate} Hz input: resampling to {sr} Hz is not implemented here")
-    full = float(1 << 15) if pcm.dtype == np.int16 else float(1 << 31)
-    x = pcm.astype(np.float32) / np.float32(full)
+    # the decoder returns right-justified samples: full scale is 2^(bps-1) whatever the container width
+    # (soundfile / librosa normalise the same way; 8-, 12-, 20- and 24-bit streams included)
+    x = pcm.astype(np.float32) / np.float32(1 << (bps - 1))
     return x if x.ndim == 1 else x.mean(axis=1, dtype=np.float32)

@@ -239,7 +239,15 @@ void parse_blob(wisb_handle* h, const std::vector<uint8_t>& head) {
     }
     uint64_t off;
     memcpy(&off, e + 88, 8);
-    WISB_REQUIRE(off < h->blob_bytes, "tensor offset outside the blob");
+    WISB_REQUIRE(t.dtype >= 0 && t.dtype <= 2 && t.ndim >= 0 && t.ndim <= 4, "bad tensor dtype / rank in the weight blob");
+    long long n_el = 1;
+    for (int k = 0; k < 4; ++k) {
+      WISB_REQUIRE(t.shape[k] >= 0 && t.shape[k] <= (1ll << 40), "bad tensor shape in the weight blob");
+      n_el *= (k < t.ndim ? t.shape[k] : 1);
+      WISB_REQUIRE(n_el <= (1ll << 40), "bad tensor shape in the weight blob");
+    }
+    const unsigned long long bytes = static_cast<unsigned long long>(n_el) * (t.dtype == 0 ? 2 : 4);
+    WISB_REQUIRE(off <= h->blob_bytes && bytes <= h->blob_bytes - off, std::string("tensor '") + name + "' reaches outside the weight blob");
     t.ptr = h->blob + off;
     h->tensors[name] = t;
   }
@@ -249,6 +257,52 @@ void parse_blob(wisb_handle* h, const std::vector<uint8_t>& head) {
   WISB_REQUIRE(d.n_mels == N_MELS && d.n_audio_ctx == T_ENC, "engine is built for 80 mels x 1500 positions");
   WISB_REQUIRE(d.n_text_ctx <= T_MAX, "n_text_ctx > 448");
   WISB_REQUIRE(d.n_langs <= 128, "more than 128 languages");
+  WISB_REQUIRE(d.n_vocab > 0 && d.n_vocab_pad >= d.n_vocab && d.n_vocab_pad % 128 == 0 && d.n_enc_layers > 0 && d.n_dec_layers > 0,
+               "bad vocabulary / layer counts in the weight blob");
+  // every tensor the kernels index must have exactly the shape the dimensions imply (a truncated or mismatched blob
+  // must fail here, not read out of bounds on the device)
+  auto expect = [&](const std::string& name, int dtype, std::initializer_list<long long> shape) {
+    auto it = h->tensors.find(name);
+    WISB_REQUIRE(it != h->tensors.end(), "weight blob is missing tensor '" + name + "'");
+    const TensorRef& t = it->second;
+    bool ok = t.dtype == dtype && t.ndim == static_cast<int>(shape.size());
+    int k = 0;
+    for (long long v : shape) ok = ok && t.shape[k++] == v;
+    WISB_REQUIRE(ok, "tensor '" + name + "' has the wrong dtype / shape for this model");
+  };
+  const long long dd = d.d_model;
+  expect("enc.conv1.w", 0, {dd, 3ll * d.n_mels});
+  expect("enc.conv2.w", 0, {dd, 3 * dd});
+  expect("enc.pos", 1, {d.n_audio_ctx, dd});
+  expect("dec.tok_emb", 0, {d.n_vocab_pad, dd});
+  expect("dec.pos", 1, {d.n_text_ctx, dd});
+  expect("dec.crosskv.w", 0, {2ll * d.n_dec_layers * dd, dd});
+  expect("dec.crosskv.b", 1, {2ll * d.n_dec_layers * dd});
+  for (int side = 0; side < 2; ++side) {
+    const int nl = side == 0 ? d.n_enc_layers : d.n_dec_layers;
+    for (int i = 0; i < nl; ++i) {
+      const std::string p = std::string(side == 0 ? "enc." : "dec.") + std::to_string(i) + ".";
+      expect(p + "qkv.w", 0, {3 * dd, dd});
+      expect(p + "qkv.b", 1, {3 * dd});
+      expect(p + "o.w", 0, {dd, dd});
+      expect(p + "o.b", 1, {dd});
+      expect(p + "fc1.w", 0, {4 * dd, dd});
+      expect(p + "fc1.b", 1, {4 * dd});
+      expect(p + "fc2.w", 0, {dd, 4 * dd});
+      expect(p + "fc2.b", 1, {dd});
+      expect(p + "ln1.g", 1, {dd});
+      expect(p + "ln2.g", 1, {dd});
+      if (side == 1) {
+        expect(p + "cq.w", 0, {dd, dd});
+        expect(p + "co.w", 0, {dd, dd});
+        expect(p + "ln3.g", 1, {dd});
+      }
+    }
+  }
+  for (const char* nm : {"meta.suppress_ids", "meta.suppress_ids_begin"}) {
+    auto it = h->tensors.find(nm);
+    WISB_REQUIRE(it != h->tensors.end() && it->second.dtype == 2 && it->second.ndim <= 1, std::string("bad '") + nm + "' in the weight blob");
+  }
 }
 
 void drop_graphs(wisb_handle* h) {
@@ -789,15 +843,14 @@ void set_extra_suppress(wisb_handle* h, const int32_t* extra, int n_extra) {
   std::vector<int> want(extra ? extra : nullptr, extra ? extra + n_extra : nullptr);
   if (want == h->mask_extra) return;
   const Dims& dm = h->dims;
+  for (int id : want) WISB_REQUIRE(id >= 0 && id < dm.n_vocab, "suppress token id outside the vocabulary");
+  h->mask_extra.assign(1, -1);  // not a valid set: if anything below fails, the next call rebuilds the mask
   WISB_CUDA(cudaMemcpyAsync(h->mask_cur.p, h->mask_base.p, dm.n_vocab, cudaMemcpyDeviceToDevice, h->stream));
   if (!want.empty()) {
     std::vector<uint8_t> m(dm.n_vocab);
     WISB_CUDA(cudaMemcpyAsync(m.data(), h->mask_base.p, dm.n_vocab, cudaMemcpyDeviceToHost, h->stream));
     WISB_CUDA(cudaStreamSynchronize(h->stream));
-    for (int id : want) {
-      WISB_REQUIRE(id >= 0 && id < dm.n_vocab, "suppress token id outside the vocabulary");
-      m[id] |= 1;
-    }
+    for (int id : want) m[id] |= 1;
     WISB_CUDA(cudaMemcpyAsync(h->mask_cur.p, m.data(), dm.n_vocab, cudaMemcpyHostToDevice, h->stream));
     WISB_CUDA(cudaStreamSynchronize(h->stream));
   }
