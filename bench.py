@@ -338,6 +338,9 @@ def run_ours(args):
     handle = _lib.Handle.from_device(blob_dev.data_ptr(), blob_dev.numel(), local, keepalive=blob_dev)
     load_s = time.time() - t0
     os.environ["WISB_DEVICE"] = str(local)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        handle.set_option(k, int(v))
 
     pcm = synth_utterance(AUDIO_SAMPLES, seed=1234 + rank)
     pcm_dev = torch.from_numpy(pcm).cuda()
@@ -751,6 +754,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="headline config only (skip configs0 / 2 / 3 / 4)")
+    ap.add_argument("--opt", action="append", default=[], help="engine option key=value (diagnostics), e.g. --opt mega_barrier=1")
     ap.add_argument("--cpu-baseline-only", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_baseline_only:

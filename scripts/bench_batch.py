@@ -35,6 +35,9 @@ def main():
     del tensors
     h = _lib.Handle.from_host(buf, 0)
     del buf
+    for kv in filter(None, os.environ.get("WISB_OPTS", "").split(",")):  # e.g. WISB_OPTS=cross_tc=0,batch_pdl=0
+        k, v = kv.split("=")
+        h.set_option(k, int(v))
     load_s = time.time() - t0
     durs = ([61440] * 22 + [160000] * 21 + [480000] * 21)
     rng = np.random.default_rng(1234)

@@ -129,6 +129,10 @@ struct BatchArgs {
   const int* flip = nullptr;
   const int* done = nullptr;      // [n_utt] or null (prefill)
   const GemmPlan* vocab = nullptr;
+  // tcgen05 cross-attention: one tensor map over the whole cross-K/V buffer viewed as [rows][64] fp16
+  int cross_tc = 1, num_sms = 148;
+  const CUtensorMap* ckv_map = nullptr;
+  const __half* ckv_base = nullptr;
 };
 // returns the number of kernels launched
 int batch_pass_run(const BatchArgs& a, const BatchLayer* layers, int n_layers, cudaStream_t stream);
@@ -174,6 +178,7 @@ struct MegaArgs {
   unsigned* cross_flags = nullptr;  // [n_utt * H][16] epoch-tagged 'partial written' flags, one 128-byte line each
   unsigned* flags = nullptr;     // grid-barrier epoch flags, one 128-byte line per CTA
   unsigned* epoch_base = nullptr;
+  int barrier_mode = 0;          // 0: per-CTA epoch flags, 1: shared counter (red.release + spin)
   unsigned long long* trace = nullptr;  // optional: [2*k] = time phase k starts, [2*k+1] = time CTA 0 reached barrier k
 };
 size_t mega_flags_words();

@@ -23,87 +23,104 @@ namespace wisb {
 
 namespace {
 
-constexpr int BD_LN_THREADS = 128;
-constexpr int BD_LN_MAX = 12;  // d_model <= 1536
+constexpr int BD_LN_WARPS = 4;   // rows per CTA (one warp per row: no block-level synchronisation at all)
+constexpr int BD_LN_MAX = 12;    // float4 per lane: d_model <= 1536
 
-__device__ __forceinline__ float block_sum_128(float v, float* s_red) {
-  v = warp_sum(v);
-  __syncthreads();  // s_red may still be read from a previous call
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  return s_red[0] + s_red[1] + s_red[2] + s_red[3];
-}
-
-// LayerNorm of the block's row held in registers (v[i] = x[tid + 128 i]) -> fp16; two-pass statistics in fp32
-__device__ __forceinline__ void row_layernorm_store(const float (&v)[BD_LN_MAX], int iters, int d, const float* __restrict__ g,
-                                                    const float* __restrict__ b, __half* __restrict__ out, float* s_red) {
-  const int tid = threadIdx.x;
+// LayerNorm of the warp's row held in registers (v[i] = float4 number lane + 32 i of the row) -> fp16;
+// two-pass statistics in fp32 (mean, then the centred sum of squares), as torch.nn.functional.layer_norm does
+__device__ __forceinline__ void row_layernorm_store(const float4 (&v)[BD_LN_MAX], int iters, int d, const float* __restrict__ g,
+                                                    const float* __restrict__ b, __half* __restrict__ out, int lane) {
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < BD_LN_MAX; ++i)
-    if (i < iters) s += v[i];
-  const float mean = block_sum_128(s, s_red) / d;
+    if (i < iters) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / d;
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < BD_LN_MAX; ++i)
     if (i < iters) {
-      const float a = v[i] - mean;
-      q = fmaf(a, a, q);
+      const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+      q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
     }
-  const float rstd = rsqrtf(block_sum_128(q, s_red) / d + 1e-5f);
+  const float rstd = rsqrtf(warp_sum(q) / d + 1e-5f);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  uint2* o2 = reinterpret_cast<uint2*>(out);
 #pragma unroll
   for (int i = 0; i < BD_LN_MAX; ++i)
     if (i < iters) {
-      const int c = tid + i * BD_LN_THREADS;
-      out[c] = __float2half_rn((v[i] - mean) * rstd * __ldg(g + c) + __ldg(b + c));
+      const float4 gg = __ldg(g4 + i * 32 + lane), bb = __ldg(b4 + i * 32 + lane);
+      __half2 h0 = __floats2half2_rn((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y);
+      __half2 h1 = __floats2half2_rn((v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&h0);
+      u.y = *reinterpret_cast<uint32_t*>(&h1);
+      o2[i * 32 + lane] = u;
     }
 }
 
 // x[r] = tok_emb[token[r]] + pos_emb[row_pos[r]];  xn[r] = LN(x[r])   (first LayerNorm of decoder layer 0)
-__global__ void __launch_bounds__(BD_LN_THREADS)
+__global__ void __launch_bounds__(BD_LN_WARPS * 32)
 bd_embed_ln_kernel(const int* __restrict__ tokens, const int* __restrict__ row_pos, const __half* __restrict__ tok_emb,
                    const float* __restrict__ pos_emb, const float* __restrict__ g, const float* __restrict__ b,
-                   float* __restrict__ x, __half* __restrict__ xn, int d) {
-  __shared__ float s_red[4];
+                   float* __restrict__ x, __half* __restrict__ xn, int d, int rows) {
   pdl_launch_dependents();
   pdl_wait();
-  const int r = blockIdx.x, tid = threadIdx.x;
-  const int iters = d / BD_LN_THREADS;
-  const __half* e = tok_emb + static_cast<long long>(tokens[r]) * d;
-  const float* p = pos_emb + static_cast<long long>(row_pos[r]) * d;
-  float v[BD_LN_MAX];
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * BD_LN_WARPS + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int iters = d / 128;
+  const uint2* e2 = reinterpret_cast<const uint2*>(tok_emb + static_cast<long long>(tokens[r]) * d);
+  const float4* p4 = reinterpret_cast<const float4*>(pos_emb + static_cast<long long>(row_pos[r]) * d);
+  float4* x4 = reinterpret_cast<float4*>(x + static_cast<long long>(r) * d);
+  float4 v[BD_LN_MAX];
 #pragma unroll
   for (int i = 0; i < BD_LN_MAX; ++i)
     if (i < iters) {
-      const int c = tid + i * BD_LN_THREADS;
-      v[i] = __half2float(e[c]) + p[c];
-      x[static_cast<long long>(r) * d + c] = v[i];
+      const uint2 eu = __ldg(e2 + i * 32 + lane);
+      const float4 pp = __ldg(p4 + i * 32 + lane);
+      const float2 e01 = __half22float2(*reinterpret_cast<const __half2*>(&eu.x));
+      const float2 e23 = __half22float2(*reinterpret_cast<const __half2*>(&eu.y));
+      v[i] = make_float4(e01.x + pp.x, e01.y + pp.y, e23.x + pp.z, e23.y + pp.w);
+      x4[i * 32 + lane] = v[i];
     }
-  row_layernorm_store(v, iters, d, g, b, xn + static_cast<long long>(r) * d, s_red);
+  row_layernorm_store(v, iters, d, g, b, xn + static_cast<long long>(r) * d, lane);
 }
 
 // x[r] += bias + sum_s partial[s][r]  (split-K slabs of the preceding GEMM, fixed summation order);  xn[r] = LN(x[r])
-__global__ void __launch_bounds__(BD_LN_THREADS)
-bd_resid_ln_kernel(float* __restrict__ x, const float* __restrict__ partial, int n_splits, long long split_stride,
+template <int NS>
+__global__ void __launch_bounds__(BD_LN_WARPS * 32)
+bd_resid_ln_kernel(float* __restrict__ x, const float* __restrict__ partial, long long split_stride,
                    const float* __restrict__ bias, const float* __restrict__ g, const float* __restrict__ b,
-                   __half* __restrict__ xn, int d) {
-  __shared__ float s_red[4];
+                   __half* __restrict__ xn, int d, int rows) {
   pdl_launch_dependents();
   pdl_wait();
-  const int r = blockIdx.x, tid = threadIdx.x;
-  const int iters = d / BD_LN_THREADS;
-  float v[BD_LN_MAX];
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * BD_LN_WARPS + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int iters = d / 128;
+  float4* x4 = reinterpret_cast<float4*>(x + static_cast<long long>(r) * d);
+  const float4* b4 = reinterpret_cast<const float4*>(bias);
+  float4 v[BD_LN_MAX];
 #pragma unroll
   for (int i = 0; i < BD_LN_MAX; ++i)
     if (i < iters) {
-      const int c = tid + i * BD_LN_THREADS;
-      const long long at = static_cast<long long>(r) * d + c;
-      float acc = __ldg(bias + c);
-      for (int s = 0; s < n_splits; ++s) acc += partial[s * split_stride + at];
-      v[i] = x[at] + acc;
-      x[at] = v[i];
+      // every load of this float4 is issued before the first add: one round trip per element whatever the split count
+      const float4 xv = x4[i * 32 + lane];
+      const float4 bv = __ldg(b4 + i * 32 + lane);
+      float4 pv[NS];
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        pv[s] = __ldcg(reinterpret_cast<const float4*>(partial + s * split_stride + static_cast<long long>(r) * d) + i * 32 + lane);
+      float4 acc = bv;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        acc.x += pv[s].x; acc.y += pv[s].y; acc.z += pv[s].z; acc.w += pv[s].w;
+      }
+      v[i] = make_float4(xv.x + acc.x, xv.y + acc.y, xv.z + acc.z, xv.w + acc.w);
+      x4[i * 32 + lane] = v[i];
     }
-  row_layernorm_store(v, iters, d, g, b, xn + static_cast<long long>(r) * d, s_red);
+  row_layernorm_store(v, iters, d, g, b, xn + static_cast<long long>(r) * d, lane);
 }
 
 // =====================================================================================================================
@@ -328,6 +345,274 @@ bd_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__ kma
   cluster.sync();  // keep every CTA's shared memory alive until the leader has read it
 }
 
+// =====================================================================================================================
+// cross-attention on tcgen05 (the default for the batched pass): persistent CTAs walk (utterance, head) items; the item's
+// K and V (2 x 1500 x 64 fp16 = 384 KB) stream ONCE through a TMA ring for all rows of the utterance.
+//   S^T = K Q^T : per 128-key tile, tcgen05.mma M=128 (keys) x N=16 (query rows, zero padded) x K=64, fp32 in TMEM
+//                 (12 tiles x 16 columns) -- keys sit on the TMEM lanes, so all 128 softmax threads have work even with
+//                 5 query rows (with queries on the lanes only 5 threads would)
+//   softmax     : thread = key; the scores of all 12 tiles of its key stay in registers (12 x rows values), one exact
+//                 row maximum / row sum over the 1500 keys (shuffles + 4-way shared memory), P^T -> fp16, swizzled smem
+//   O^T = V^T P : tcgen05.mma M=64 (head dim; A = the V tile as loaded, MN-major) x N=16 x K=128 per tile, accumulated
+//                 over the 12 tiles in TMEM; rows are scaled by 1/rowsum on the way out
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = softmax / epilogue.  Finished utterances are skipped.
+// =====================================================================================================================
+constexpr int XT_THREADS = 192;
+constexpr int XT_TILE = 128 * HEAD_DIM * 2;        // 16 KB: 128 keys of K or of V
+constexpr int XT_STAGES = 8;
+constexpr int XT_NT = T_ENC_PAD / 128;             // 12 key tiles per item
+constexpr int XT_NQ = 16;                          // query rows padded to the MMA N
+constexpr int XT_P_TILE = XT_NQ * 128 * 2;         // 4 KB: P^T [16 rows][128 keys] = two swizzled 64-key halves
+constexpr int XT_Q_BYTES = XT_NQ * HEAD_DIM * 2;   // 2 KB
+constexpr int XT_OFF_P = XT_STAGES * XT_TILE;
+constexpr int XT_OFF_Q = XT_OFF_P + XT_NT * XT_P_TILE;
+constexpr int XT_OFF_BAR = XT_OFF_Q + 2 * XT_Q_BYTES;
+constexpr int XT_SMEM = XT_OFF_BAR + 1024 + 1024;  // + barriers / scratch (720 B) + alignment slack
+constexpr int XT_D2_COL = XT_NT * XT_NQ;           // 192: O^T accumulator columns
+constexpr float XT_LOG2E = 1.4426950408889634f;
+
+template <int NB>
+__global__ void __launch_bounds__(XT_THREADS, 1)
+bd_cross_attn_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const float* __restrict__ q, long long row_k0,
+                        long long row_v0, const int* __restrict__ done, __half* __restrict__ ctx, int n_utt,
+                        int rows_per_utt, int d, int H) {
+  extern __shared__ uint8_t xt_raw[];
+  const uint32_t raw_addr = smem_u32(xt_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = xt_raw + (base - raw_addr);
+  const uint32_t sP = base + XT_OFF_P, sQ = base + XT_OFF_Q;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + XT_OFF_BAR);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (XT_STAGES + s); };
+  const uint32_t q_full0 = bar0 + 8u * (2 * XT_STAGES);  // [2]
+  const uint32_t s_full = q_full0 + 16, d1_empty = q_full0 + 24, p_full = q_full0 + 32, d2_empty = q_full0 + 40,
+                 o_full = q_full0 + 48;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * XT_STAGES + 8);
+  float* s_red = reinterpret_cast<float*>(bars + 2 * XT_STAGES + 10);  // [2][4][8] row max / row sum partials
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < XT_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(q_full0, 4);
+    mbar_init(q_full0 + 8, 4);
+    mbar_init(s_full, 1);
+    mbar_init(d1_empty, 4);
+    mbar_init(p_full, 4);
+    mbar_init(d2_empty, 4);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&map_kv);
+  }
+  // P^T and Q^T rows beyond the live query rows are zero for the whole kernel
+  for (int i = threadIdx.x; i < (XT_NT * XT_P_TILE + 2 * XT_Q_BYTES) / 16; i += XT_THREADS)
+    *reinterpret_cast<uint4*>(smem + XT_OFF_P + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+  if (warp == 1) {
+    tmem_alloc<256>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // q and the `done` flags come from the previous kernels of the chain
+
+  const int n_items = n_utt * H;
+  auto item_live = [&](int item) { return done == nullptr || done[item / H] == 0; };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer: K tiles, then V tiles of every item
+    if (lane == 0) {
+      unsigned unit = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        if (!item_live(item)) continue;
+        for (int kv = 0; kv < 2; ++kv) {
+          const long long row0 = (kv == 0 ? row_k0 : row_v0) + static_cast<long long>(item) * T_ENC_PAD;
+          for (int j = 0; j < XT_NT; ++j, ++unit) {
+            const int st = unit % XT_STAGES;
+            mbar_wait(empty_bar(st), ((unit / XT_STAGES) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(full_bar(st), XT_TILE);
+            tma_load_2d(base + st * XT_TILE, &map_kv, full_bar(st), 0, static_cast<int>(row0 + j * 128));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_f16(128, XT_NQ, false, false);
+      constexpr uint32_t idesc_o = make_idesc_f16(64, XT_NQ, true, false);  // A = V tile, MN-major (head dim contiguous)
+      unsigned unit = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        if (!item_live(item)) continue;
+        mbar_wait(q_full0 + 8u * (it & 1), (it >> 1) & 1u);
+        if (it > 0) mbar_wait(d1_empty, (it - 1) & 1u);
+        tc_fence_after();
+        const uint32_t qb = sQ + (it & 1) * XT_Q_BYTES;
+        for (int j = 0; j < XT_NT; ++j, ++unit) {
+          const int st = unit % XT_STAGES;
+          mbar_wait(full_bar(st), (unit / XT_STAGES) & 1u);
+          tc_fence_after();
+          const uint64_t da = make_desc_sw128(base + st * XT_TILE, 1024);
+          const uint64_t db = make_desc_sw128(qb, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tmem_base + static_cast<uint32_t>(j * XT_NQ), da + 2u * k, db + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(empty_bar(st));
+        }
+        umma_commit(s_full);
+        mbar_wait(p_full, it & 1u);
+        if (it > 0) mbar_wait(d2_empty, (it - 1) & 1u);
+        tc_fence_after();
+        for (int j = 0; j < XT_NT; ++j, ++unit) {
+          const int st = unit % XT_STAGES;
+          mbar_wait(full_bar(st), (unit / XT_STAGES) & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t dv = make_desc_sw128(base + st * XT_TILE + k * 2048, 1024);
+            const uint64_t dp = make_desc_sw128(sP + j * XT_P_TILE + (k >> 2) * 2048, 1024) + 2u * (k & 3);
+            umma_f16_ss(tmem_base + XT_D2_COL, dv, dp, idesc_o, (j | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(st));
+        }
+        umma_commit(o_full);
+        ++it;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax / epilogue: 128 threads = 128 keys of a tile
+    const int qd = warp & 3;                       // TMEM lane quarter this warp may access
+    const int key = qd * 32 + lane;                // key inside a tile == TMEM lane
+    const int st_tid = (warp - 2) * 32 + lane;     // 0..127
+    const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    auto soft_sync = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
+    auto write_q = [&](int item, int buf) {
+      // Q rows of the item -> fp16, pre-scaled by head_dim^-0.5 (exact), K-major 128-byte-swizzled rows
+      const int u = item / H, h = item - u * H;
+      if (st_tid < rows_per_utt * 8) {
+        const int r = st_tid >> 3, c = st_tid & 7;
+        const float* qr = q + static_cast<long long>(u * rows_per_utt + r) * d + h * HEAD_DIM + c * 8;
+        const float4 a0 = *reinterpret_cast<const float4*>(qr), a1 = *reinterpret_cast<const float4*>(qr + 4);
+        __half2 h0 = __floats2half2_rn(a0.x * 0.125f, a0.y * 0.125f), h1 = __floats2half2_rn(a0.z * 0.125f, a0.w * 0.125f);
+        __half2 h2 = __floats2half2_rn(a1.x * 0.125f, a1.y * 0.125f), h3 = __floats2half2_rn(a1.z * 0.125f, a1.w * 0.125f);
+        uint4 v4;
+        v4.x = *reinterpret_cast<uint32_t*>(&h0); v4.y = *reinterpret_cast<uint32_t*>(&h1);
+        v4.z = *reinterpret_cast<uint32_t*>(&h2); v4.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(smem + XT_OFF_Q + buf * XT_Q_BYTES + r * 128 + ((c ^ (r & 7)) << 4)) = v4;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_full0 + 8u * buf);
+    };
+    auto next_live = [&](int item) {
+      item += gridDim.x;
+      while (item < n_items && !item_live(item)) item += gridDim.x;
+      return item;
+    };
+    int item = blockIdx.x;
+    while (item < n_items && !item_live(item)) item += gridDim.x;
+    if (item < n_items) write_q(item, 0);
+    int it = 0;
+    for (; item < n_items; ++it) {
+      const int nxt = next_live(item);
+      if (nxt < n_items) write_q(nxt, (it + 1) & 1);  // that buffer's last reader (MMA1 of item it-1) is done
+      mbar_wait(s_full, it & 1u);
+      tc_fence_after();
+      float sc[XT_NT][NB];
+#pragma unroll
+      for (int j = 0; j < XT_NT; ++j) {
+        uint32_t v[8];
+        tmem_ld_32x32b_x8(tmem_base + lane_off + static_cast<uint32_t>(j * XT_NQ), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int r = 0; r < NB; ++r) sc[j][r] = __uint_as_float(v[r]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d1_empty);
+      // keys >= 1500 are padding rows of the window
+#pragma unroll
+      for (int r = 0; r < NB; ++r)
+        if ((XT_NT - 1) * 128 + key >= T_ENC) sc[XT_NT - 1][r] = -INFINITY;
+      // exact row maximum over all keys
+      float mx[NB];
+#pragma unroll
+      for (int r = 0; r < NB; ++r) {
+        float m = sc[0][r];
+#pragma unroll
+        for (int j = 1; j < XT_NT; ++j) m = fmaxf(m, sc[j][r]);
+        mx[r] = warp_max(m);
+      }
+      float* red = s_red + (it & 1) * 64;
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < NB; ++r) red[(warp - 2) * 8 + r] = mx[r];
+      }
+      soft_sync();
+#pragma unroll
+      for (int r = 0; r < NB; ++r) mx[r] = fmaxf(fmaxf(red[r], red[8 + r]), fmaxf(red[16 + r], red[24 + r])) * XT_LOG2E;
+      // probabilities -> P^T tiles (fp16), row sums
+      float sum[NB];
+#pragma unroll
+      for (int r = 0; r < NB; ++r) sum[r] = 0.f;
+      const int half = key >> 6, kk = key & 63;
+      const uint32_t p_off = XT_OFF_P + half * 2048 + (kk & 7) * 2;
+#pragma unroll
+      for (int j = 0; j < XT_NT; ++j) {
+#pragma unroll
+        for (int r = 0; r < NB; ++r) {
+          const float pr = exp2f(fmaf(sc[j][r], XT_LOG2E, -mx[r]));
+          const __half ph = __float2half_rn(pr);
+          sum[r] += __half2float(ph);  // the sum of what the tensor core will actually multiply
+          if (r < rows_per_utt)
+            *reinterpret_cast<__half*>(smem + p_off + j * XT_P_TILE + r * 128 + (((kk >> 3) ^ (r & 7)) << 4)) = ph;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NB; ++r) sum[r] = warp_sum(sum[r]);
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < NB; ++r) red[32 + (warp - 2) * 8 + r] = sum[r];
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      soft_sync();
+      // epilogue: O^T [64 dims x rows]; with M = 64 the accumulator occupies lanes 0..15 of every 32-lane quarter
+      mbar_wait(o_full, it & 1u);
+      tc_fence_after();
+      uint32_t ov[8];
+      tmem_ld_32x32b_x8(tmem_base + lane_off + XT_D2_COL, ov);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d2_empty);
+      if (lane < 16) {
+        const int u = item / H, h = item - u * H;
+        const int e = qd * 16 + lane;
+#pragma unroll
+        for (int r = 0; r < NB; ++r) {
+          if (r < rows_per_utt) {
+            const float l = (red[32 + r] + red[40 + r]) + (red[48 + r] + red[56 + r]);
+            ctx[static_cast<long long>(u * rows_per_utt + r) * d + h * HEAD_DIM + e] = __float2half_rn(__uint_as_float(ov[r]) / l);
+          }
+        }
+      }
+      item = nxt;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem_base);
+}
+
 template <typename Kern, typename... Args>
 void bd_launch(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args... args) {
   cudaLaunchConfig_t cfg{};
@@ -345,7 +630,25 @@ void bd_launch(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t strea
 
 int bd_ca_smem(int nb) { return 2 * BD_CA_KEYS * HEAD_DIM * 2 + BD_CA_GROUPS * nb * HEAD_DIM * 4; }
 
+template <int NB>
+void cross_tc_launch(const BatchArgs& a, const BatchLayer& ly, cudaStream_t s) {
+  static std::atomic<unsigned long long> once{0};
+  once_per_device(once, [] {
+    WISB_CUDA(cudaFuncSetAttribute(bd_cross_attn_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, XT_SMEM));
+  });
+  const int items = a.n_utt * a.H;
+  const long long row_k0 = (ly.ck - a.ckv_base) / HEAD_DIM, row_v0 = (ly.cv - a.ckv_base) / HEAD_DIM;
+  bd_launch(bd_cross_attn_tc_kernel<NB>, dim3(items < a.num_sms ? items : a.num_sms), dim3(XT_THREADS), XT_SMEM, s, a.pdl != 0,
+            *a.ckv_map, a.q, row_k0, row_v0, a.done, a.ctx, a.n_utt, a.rows_per_utt, a.d, a.H);
+}
+
 void cross_attn_launch(const BatchArgs& a, const BatchLayer& ly, cudaStream_t s) {
+  if (a.cross_tc) {
+    if (a.rows_per_utt <= 1) cross_tc_launch<1>(a, ly, s);
+    else if (a.rows_per_utt <= 5) cross_tc_launch<5>(a, ly, s);
+    else cross_tc_launch<MAX_BEAM>(a, ly, s);
+    return;
+  }
   static std::atomic<unsigned long long> once{0};
   once_per_device(once, [&] {
     WISB_CUDA(cudaFuncSetAttribute(bd_cross_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bd_ca_smem(1)));
@@ -362,6 +665,18 @@ void cross_attn_launch(const BatchArgs& a, const BatchLayer& ly, cudaStream_t s)
     bd_launch(bd_cross_attn_kernel<MAX_BEAM>, grid, dim3(BD_CA_THREADS), bd_ca_smem(MAX_BEAM), s, a.pdl != 0, a.q, ly.ck, ly.cv, a.done, a.ctx, rpu, a.d, a.H);
 }
 
+void resid_ln_launch(const BatchArgs& a, int n_splits, const float* bias, const float* g, const float* b, cudaStream_t s) {
+  const dim3 grid(cdiv(a.R, BD_LN_WARPS)), block(BD_LN_WARPS * 32);
+  const bool pdl = a.pdl != 0;
+  switch (n_splits) {
+    case 1: bd_launch(bd_resid_ln_kernel<1>, grid, block, 0, s, pdl, a.x, a.part, a.part_stride, bias, g, b, a.xn, a.d, a.R); break;
+    case 2: bd_launch(bd_resid_ln_kernel<2>, grid, block, 0, s, pdl, a.x, a.part, a.part_stride, bias, g, b, a.xn, a.d, a.R); break;
+    case 4: bd_launch(bd_resid_ln_kernel<4>, grid, block, 0, s, pdl, a.x, a.part, a.part_stride, bias, g, b, a.xn, a.d, a.R); break;
+    case 8: bd_launch(bd_resid_ln_kernel<8>, grid, block, 0, s, pdl, a.x, a.part, a.part_stride, bias, g, b, a.xn, a.d, a.R); break;
+    default: throw Error(1, "batched decoder pass: split-K factor must be 1, 2, 4 or 8");
+  }
+}
+
 void run_gemm_rows(const GemmPlan& plan, int rows, int pdl, cudaStream_t s) {
   GemmPlan p = plan;  // the plan is built for the buffer capacity; this pass uses the first `rows` rows
   p.M = round_up(rows, 128);
@@ -376,12 +691,12 @@ void run_gemm_rows(const GemmPlan& plan, int rows, int pdl, cudaStream_t s) {
 int batch_pass_run(const BatchArgs& a, const BatchLayer* layers, int n_layers, cudaStream_t s) {
   WISB_REQUIRE(a.R >= 1 && a.R == a.n_utt * a.rows_per_utt, "batched decoder pass: rows must be utterances x rows per utterance");
   WISB_REQUIRE(a.rows_per_utt >= 1 && a.rows_per_utt <= MAX_BEAM, "batched decoder pass: 1..8 rows per utterance");
-  WISB_REQUIRE(a.d % BD_LN_THREADS == 0 && a.d <= BD_LN_THREADS * BD_LN_MAX, "batched decoder pass: d_model multiple of 128, <= 1536");
+  WISB_REQUIRE(a.d % 128 == 0 && a.d <= 128 * BD_LN_MAX, "batched decoder pass: d_model multiple of 128, <= 1536");
   WISB_REQUIRE(a.t_ind <= BD_SA_TMAX, "batched decoder pass: more than 448 text positions");
   const bool pdl = a.pdl != 0;
   int n = 0;
-  bd_launch(bd_embed_ln_kernel, dim3(a.R), dim3(BD_LN_THREADS), 0, s, pdl, a.tokens, a.row_pos, a.tok_emb, a.pos_emb,
-            layers[0].ln1g, layers[0].ln1b, a.x, a.xn, a.d);
+  bd_launch(bd_embed_ln_kernel, dim3(cdiv(a.R, BD_LN_WARPS)), dim3(BD_LN_WARPS * 32), 0, s, pdl, a.tokens, a.row_pos, a.tok_emb,
+            a.pos_emb, layers[0].ln1g, layers[0].ln1b, a.x, a.xn, a.d, a.R);
   ++n;
   for (int i = 0; i < n_layers; ++i) {
     const BatchLayer& ly = layers[i];
@@ -389,17 +704,14 @@ int batch_pass_run(const BatchArgs& a, const BatchLayer* layers, int n_layers, c
     bd_launch(bd_self_attn_kernel, dim3(cdiv(a.H, 4), a.R), dim3(128), 0, s, pdl, a.q, ly.kcache, ly.vcache, a.row_pos,
               a.row_slot, a.indir0, a.indir1, a.flip, a.done, a.ctx, a.d, a.H, a.t_cap, a.t_ind, a.rows_per_utt, a.prefill);
     run_gemm_rows(ly.o, a.R, a.pdl, s);
-    bd_launch(bd_resid_ln_kernel, dim3(a.R), dim3(BD_LN_THREADS), 0, s, pdl, a.x, a.part, ly.o.k_splits, a.part_stride,
-              ly.ob, ly.ln2g, ly.ln2b, a.xn, a.d);
+    resid_ln_launch(a, ly.o.k_splits, ly.ob, ly.ln2g, ly.ln2b, s);
     run_gemm_rows(ly.cq, a.R, a.pdl, s);
     cross_attn_launch(a, ly, s);
     run_gemm_rows(ly.co, a.R, a.pdl, s);
-    bd_launch(bd_resid_ln_kernel, dim3(a.R), dim3(BD_LN_THREADS), 0, s, pdl, a.x, a.part, ly.co.k_splits, a.part_stride,
-              ly.cob, ly.ln3g, ly.ln3b, a.xn, a.d);
+    resid_ln_launch(a, ly.co.k_splits, ly.cob, ly.ln3g, ly.ln3b, s);
     run_gemm_rows(ly.fc1, a.R, a.pdl, s);
     run_gemm_rows(ly.fc2, a.R, a.pdl, s);
-    bd_launch(bd_resid_ln_kernel, dim3(a.R), dim3(BD_LN_THREADS), 0, s, pdl, a.x, a.part, ly.fc2.k_splits, a.part_stride,
-              ly.fc2b, ly.next_g, ly.next_b, a.xn, a.d);
+    resid_ln_launch(a, ly.fc2.k_splits, ly.fc2b, ly.next_g, ly.next_b, s);
     n += 11;
   }
   if (a.with_logits) {

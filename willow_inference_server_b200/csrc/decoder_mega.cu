@@ -215,10 +215,22 @@ __device__ __forceinline__ void grid_barrier(const MegaArgs& A, unsigned& epoch,
   if (A.trace != nullptr && blockIdx.x == 0 && ctid == 0) A.trace[2 * (epoch - epoch0) + 1] = globaltimer_ns();
   cons_sync();
   ++epoch;
-  if (ctid == 0) st_release_gpu(A.flags + blockIdx.x * 32, epoch);
-  if (ctid < static_cast<int>(gridDim.x)) {
-    const unsigned* f = A.flags + ctid * 32;
-    while (static_cast<int>(ld_acquire_gpu(f) - epoch) < 0) {
+  if (A.barrier_mode == 1) {
+    // one release-add per CTA on a shared counter, thread 0 spins on it (scripts/ubench_sync: 1.23 us vs 1.54 us for the
+    // flag barrier on 148 CTAs); the counter equals epoch * gridDim.x whenever all CTAs have passed barrier `epoch`
+    if (ctid == 0) {
+      unsigned* counter = A.epoch_base + 8;
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+      const unsigned target = epoch * gridDim.x;
+      while (static_cast<int>(ld_acquire_gpu(counter) - target) < 0) {
+      }
+    }
+  } else {
+    if (ctid == 0) st_release_gpu(A.flags + blockIdx.x * 32, epoch);
+    if (ctid < static_cast<int>(gridDim.x)) {
+      const unsigned* f = A.flags + ctid * 32;
+      while (static_cast<int>(ld_acquire_gpu(f) - epoch) < 0) {
+      }
     }
   }
   cons_sync();
@@ -846,7 +858,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs 
   if (A.with_logits) consume_gemv<NR>(rg, A, A.vocab, nullptr, ctid, s_red, s_stat);
   // publish the final epoch for the next launch (every CTA leaves the same value behind)
   grid_barrier(A, epoch, ctid, epoch0);
-  if (blockIdx.x == 0 && ctid == 0) *A.epoch_base = epoch;
+  if (blockIdx.x == 0 && ctid == 0) {
+    *A.epoch_base = epoch;
+    A.epoch_base[8] = epoch * gridDim.x;  // keeps the counter of the atomic barrier mode in step whatever mode ran
+  }
 }
 
 __global__ void chunk_major_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int N, int K, int n_chunks) {

@@ -121,6 +121,7 @@ struct wisb_handle {
   DevBuf<__half> h1, xn, qkv, vt, ctx, hbuf, enc_out, ckv;
   DevBuf<float> x;
   GemmPlan plan_conv2, plan_ckv;
+  CUtensorMap ckv_map;
   std::vector<EncLayerPlans> enc_plans;
   AttnPlan attn_plan;
   int plans_B = 0, plans_vmn = -1;
@@ -136,7 +137,7 @@ struct wisb_handle {
   DevBuf<int> row_pos, row_slot, max_new_u;
   int search_rows = 0;  // rows the search / state buffers above are sized for
   // batched decoder pass (more than DEC_MAX_ROWS rows): workspaces for bd_rows (multiple of 128) rows, bd_tcap positions
-  int batch_rows = 320, batch_pdl = 1, decoder_batch = 1;  // options: row capacity of one shared pass; programmatic dependent launch
+  int batch_rows = 320, batch_pdl = 1, decoder_batch = 1, mega_barrier = 0, cross_tc = 1;  // options: row capacity of one shared pass; programmatic dependent launch
   int bd_rows = 0, bd_tcap = 0, bd_launches_step = 0;
   DevBuf<float> bx, bq, bpart, blogits;
   DevBuf<__half> bxn, bctx, bh, bkc, bvc;
@@ -441,6 +442,7 @@ void ensure_encoder(wisb_handle* h, int B) {
   const long long M = static_cast<long long>(B) * T_ENC_PAD;
   if (B > h->enc_cap) {
     h->plans_B = 0;
+    drop_graphs(h);  // captured decoder graphs hold pointers into the buffers reallocated below
     h->h1.release();
     h->h1.ensure((static_cast<size_t>(B) * H1_ROWS + 8) * d, true);
     h->x.ensure(M * d, true);
@@ -451,6 +453,8 @@ void ensure_encoder(wisb_handle* h, int B) {
     h->hbuf.ensure(M * 4 * d, true);
     h->enc_out.ensure(M * d, true);
     h->ckv.ensure(static_cast<size_t>(dm.n_dec_layers) * 2 * M * d, true);
+    // the whole cross-K/V buffer as rows of one head's 64 values (for the tcgen05 cross-attention of the batched pass)
+    make_tmap_f16_2d(&h->ckv_map, h->ckv.p, HEAD_DIM, static_cast<long long>(h->ckv.n / HEAD_DIM), HEAD_DIM, HEAD_DIM, 128);
     h->enc_cap = B;
   }
   if (h->plans_B == B && h->plans_vmn == h->attn_v_mn) return;
@@ -731,6 +735,7 @@ int enqueue_decoder_forward_mega(wisb_handle* h, const DecodeCfg& c, bool with_l
   a.cross_flags = h->cross_flags.p;
   a.flags = h->mega_flags.p;
   a.epoch_base = h->mega_flags.p + 160 * 32;
+  a.barrier_mode = h->mega_barrier;
   if (h->mega_trace_on) {
     h->mega_trace.ensure(2048, true);
     a.trace = h->mega_trace.p;
@@ -1040,6 +1045,10 @@ BatchArgs make_batch_args(wisb_handle* h, const DecodeCfg& c) {
   a.indir1 = h->ind1.p;
   a.flip = h->flip.p;
   a.vocab = &h->bd_vocab;
+  a.cross_tc = h->cross_tc;
+  a.num_sms = h->num_sms;
+  a.ckv_map = &h->ckv_map;
+  a.ckv_base = h->ckv.p;
   return a;
 }
 
@@ -1320,6 +1329,11 @@ int wisb_set_option(wisb_handle* h, const char* key, int value) {
       h->batch_rows = value;
     }
     else if (k == "batch_pdl") h->batch_pdl = value ? 1 : 0;
+    else if (k == "mega_barrier") h->mega_barrier = value ? 1 : 0;
+    else if (k == "cross_tc") {  // 1: tcgen05 cross-attention in the batched pass, 0: the SIMT cluster kernel (cross-check)
+      h->cross_tc = value ? 1 : 0;
+      drop_graphs(h);
+    }
     else if (k == "decoder_batch") h->decoder_batch = value;  // 2 = use the batched pass even for <= 8 rows (tests)
     else throw Error(1, "unknown option '" + k + "'");
   });

@@ -52,6 +52,10 @@ void gemm_run(const GemmPlan& p, cudaStream_t stream);
 // slow SIMT cross-check used only by the diagnostics entry point / tests
 void gemm_ref_run(const __half* a, long long lda, const __half* w, float* c, int M, int N, int K, cudaStream_t stream);
 
+// 2-D fp16 tensor map: inner dimension `cols` (contiguous), `rows` rows of stride `ld` elements, 128B swizzle
+void make_tmap_f16_2d(CUtensorMap* map, const void* ptr, long long cols, long long rows, long long ld, int box_cols,
+                      int box_rows);
+
 // ------------------------------------------------------------------ log-mel front end (logmel.cu)
 // pcm: B utterances, f32 or s16, utterance b starts at pcm + offsets[b] (elements) and has n_samples[b] samples
 // (unpadded; padding / trimming to 480000 is fused).  mel: [B, 80, 3000] f32 on device.
