@@ -65,6 +65,20 @@ def main():
                                 "logmel_ms": round(tl, 2), "encoder_ms": round(t["encoder_ms"], 1), "cross_kv_ms": round(t["cross_kv_ms"], 1),
                                 "decode_ms": round(t["decode_ms"], 1), "passes": int(t["decode_steps"]), "launches": int(t["launches"]),
                                 "x_realtime_dev": round(audio_s / ((tl + t["generate_ms"]) * 1e-3), 1)})
+    if os.environ.get("WISB_PROFILE"):
+        # per-kernel-family CUDA-event sums (eager launches): a run with 2 generated tokens and a full run; the difference
+        # is the decode loop alone.  gemm / cross-attention / LayerNorm+embed / self-attention (+ conv1 on the encoder side)
+        h.set_option("profile", 1)
+        prof = {}
+        for name, ml in (("short", np.full(B, 6, np.int32)), ("full", max_len)):
+            h.logmel(flat, off, ns, to_host=False, keep=True)
+            h.generate(None, np.asarray([PROMPT] * B, np.int32), 5, 1.0, 1.0, ml, [dims.eot], B=B)
+            t = h.timing()
+            prof[name] = {k: round(t[k], 2) for k in ("gemm_ms", "attn_ms", "ln_ms", "conv1_ms", "decode_ms", "encoder_ms", "decode_steps")}
+        prof["decode_only"] = {k: round(prof["full"][k] - prof["short"][k], 2) for k in prof["full"]}
+        prof["legend"] = "decode_only: gemm_ms = tcgen05 GEMMs, attn_ms = cross-attention, ln_ms = LayerNorm/residual/embed, conv1_ms = self-attention"
+        out["profile"] = prof
+        h.set_option("profile", 0)
     print(json.dumps(out))
 
 

@@ -85,3 +85,56 @@ def test_handles_coexist_and_threads(large):
     assert not errors
     assert results["s1"] == want_small and results["s2"] == want_small and results["l"] == want_large
     hs.close()
+
+
+def test_large_v2_numeric_parity_against_the_oracle():
+    """Full-size (d_model 1280, 32 + 32 layers) numeric parity: encoder output, teacher-forced logits and a beam-5 decode
+    whose hypotheses finish on their own (<|endoftext|> NOT suppressed), against the fp32 oracle on the same weights.
+    Tolerances (fp16 tensor-core operands, fp32 accumulation, 32 layers deep): encoder output <= 6e-2 abs (values O(1)),
+    logits <= 2.5e-1 abs on logits that span about +-60 (peaked model), tokens exact when the oracle's transcript is a
+    robust decision."""
+    from oracle import logmel as om
+    from oracle.whisper_ref import WhisperOracle
+    from tests.gpu_common import LOGIT_TOL, RAMP, SCRIPT
+
+    dims = W.WhisperDims.for_size("large-v2")
+    tensors = W.synth_engine_tensors(dims, seed=3, eot_ramp=RAMP, script=SCRIPT)
+    buf = np.zeros(W.blob_nbytes(tensors), np.uint8)
+    W.write_blob_into(buf, dims, tensors)
+    h = _lib.Handle.from_host(buf, 0)
+    del buf
+    oracle = WhisperOracle(dims, tensors)
+    del tensors
+    pcm = [_synth(61440, 21), _synth(160000, 22)]
+    mel = om.log_mel_batch(pcm)
+    enc = oracle.encode(mel)
+    got_enc = h.debug_encode(mel)
+    enc_err = float(np.abs(got_enc - enc.numpy()).max())
+    toks = PROMPT + [1000, 2000, 30000, 41000, 12, 50000]
+    want = oracle.forced_logits(enc[0], toks).numpy()
+    got = h.debug_forced_logits(mel[:1], toks)           # persistent SIMT pass (fp32 activations)
+    h.set_option("decoder_batch", 2)
+    got_b = h.debug_forced_logits(mel[:1], toks)         # batched pass (fp16 GEMM operands, tcgen05)
+    h.set_option("decoder_batch", 1)
+    err, err_b = float(np.abs(got - want).max()), float(np.abs(got_b - want).max())
+    print(f"large-v2: encoder max abs err {enc_err:.4f}; logits err {err:.4f} (SIMT pass) {err_b:.4f} (batched pass); "
+          f"logit range [{want.min():.1f}, {want.max():.1f}]")
+    assert enc_err <= 6e-2
+    assert err <= 2.5e-1 and err_b <= 2.5e-1
+    # beam-5 decode, hypotheses finish through the <|endoftext|> ramp (finished pool, early stop, length normalisation)
+    base = oracle.generate(mel, [PROMPT] * 2, beam_size=5, enc=enc)
+    probe = oracle.generate(mel, [PROMPT] * 2, beam_size=5, enc=enc, logit_noise=(LOGIT_TOL, 77))
+    m = models.Whisper(None, device="cuda", _handles=[h])
+    # one utterance per call: 5 rows, the persistent SIMT pass
+    out = [m.generate(models.StorageView.from_array(mel[i : i + 1]), [PROMPT], beam_size=5, return_scores=True)[0] for i in range(2)]
+    robust = [i for i in range(2) if base[i].sequences_ids == probe[i].sequences_ids]
+    assert robust, "neither full-size oracle transcript is a robust decision"
+    for i in robust:
+        assert out[i].sequences_ids[0] == base[i].sequences_ids[0], i
+        assert 5 <= len(out[i].sequences_ids[0]) < 40
+        assert abs(out[i].scores[0] - base[i].scores[0]) < 5e-2
+    # the same two utterances as rows of one batched pass (10 rows: tcgen05 GEMM chain + tcgen05 cross-attention)
+    outb = m.generate(models.StorageView.from_array(mel), [PROMPT] * 2, beam_size=5)
+    for i in robust:
+        assert outb[i].sequences_ids[0] == base[i].sequences_ids[0], i
+    h.close()

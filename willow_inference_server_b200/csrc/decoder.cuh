@@ -133,6 +133,10 @@ struct BatchArgs {
   int cross_tc = 1, num_sms = 148;
   const CUtensorMap* ckv_map = nullptr;
   const __half* ckv_base = nullptr;
+  // optional per-kernel-family timing hook (engine option "profile", eager launches only):
+  // cat 0 GEMM, 1 cross-attention, 2 LayerNorm / embedding, 3 self-attention; begin = 1 / 0
+  void (*prof)(void* ctx, int cat, int begin) = nullptr;
+  void* prof_ctx = nullptr;
 };
 // returns the number of kernels launched
 int batch_pass_run(const BatchArgs& a, const BatchLayer* layers, int n_layers, cudaStream_t stream);

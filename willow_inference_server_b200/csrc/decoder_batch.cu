@@ -694,28 +694,54 @@ int batch_pass_run(const BatchArgs& a, const BatchLayer* layers, int n_layers, c
   WISB_REQUIRE(a.d % 128 == 0 && a.d <= 128 * BD_LN_MAX, "batched decoder pass: d_model multiple of 128, <= 1536");
   WISB_REQUIRE(a.t_ind <= BD_SA_TMAX, "batched decoder pass: more than 448 text positions");
   const bool pdl = a.pdl != 0;
+  struct Scope {  // brackets one kernel with the optional timing hook
+    const BatchArgs& a;
+    Scope(const BatchArgs& a_, int cat) : a(a_) {
+      if (a.prof) a.prof(a.prof_ctx, cat, 1);
+    }
+    ~Scope() {
+      if (a.prof) a.prof(a.prof_ctx, 0, 0);
+    }
+  };
   int n = 0;
-  bd_launch(bd_embed_ln_kernel, dim3(cdiv(a.R, BD_LN_WARPS)), dim3(BD_LN_WARPS * 32), 0, s, pdl, a.tokens, a.row_pos, a.tok_emb,
-            a.pos_emb, layers[0].ln1g, layers[0].ln1b, a.x, a.xn, a.d, a.R);
+  {
+    Scope t(a, 2);
+    bd_launch(bd_embed_ln_kernel, dim3(cdiv(a.R, BD_LN_WARPS)), dim3(BD_LN_WARPS * 32), 0, s, pdl, a.tokens, a.row_pos, a.tok_emb,
+              a.pos_emb, layers[0].ln1g, layers[0].ln1b, a.x, a.xn, a.d, a.R);
+  }
   ++n;
+  auto gemm = [&](const GemmPlan& p) {
+    Scope t(a, 0);
+    run_gemm_rows(p, a.R, a.pdl, s);
+  };
+  auto ln = [&](int splits, const float* bias, const float* g, const float* b) {
+    Scope t(a, 2);
+    resid_ln_launch(a, splits, bias, g, b, s);
+  };
   for (int i = 0; i < n_layers; ++i) {
     const BatchLayer& ly = layers[i];
-    run_gemm_rows(ly.qkv, a.R, a.pdl, s);
-    bd_launch(bd_self_attn_kernel, dim3(cdiv(a.H, 4), a.R), dim3(128), 0, s, pdl, a.q, ly.kcache, ly.vcache, a.row_pos,
-              a.row_slot, a.indir0, a.indir1, a.flip, a.done, a.ctx, a.d, a.H, a.t_cap, a.t_ind, a.rows_per_utt, a.prefill);
-    run_gemm_rows(ly.o, a.R, a.pdl, s);
-    resid_ln_launch(a, ly.o.k_splits, ly.ob, ly.ln2g, ly.ln2b, s);
-    run_gemm_rows(ly.cq, a.R, a.pdl, s);
-    cross_attn_launch(a, ly, s);
-    run_gemm_rows(ly.co, a.R, a.pdl, s);
-    resid_ln_launch(a, ly.co.k_splits, ly.cob, ly.ln3g, ly.ln3b, s);
-    run_gemm_rows(ly.fc1, a.R, a.pdl, s);
-    run_gemm_rows(ly.fc2, a.R, a.pdl, s);
-    resid_ln_launch(a, ly.fc2.k_splits, ly.fc2b, ly.next_g, ly.next_b, s);
+    gemm(ly.qkv);
+    {
+      Scope t(a, 3);
+      bd_launch(bd_self_attn_kernel, dim3(cdiv(a.H, 4), a.R), dim3(128), 0, s, pdl, a.q, ly.kcache, ly.vcache, a.row_pos,
+                a.row_slot, a.indir0, a.indir1, a.flip, a.done, a.ctx, a.d, a.H, a.t_cap, a.t_ind, a.rows_per_utt, a.prefill);
+    }
+    gemm(ly.o);
+    ln(ly.o.k_splits, ly.ob, ly.ln2g, ly.ln2b);
+    gemm(ly.cq);
+    {
+      Scope t(a, 1);
+      cross_attn_launch(a, ly, s);
+    }
+    gemm(ly.co);
+    ln(ly.co.k_splits, ly.cob, ly.ln3g, ly.ln3b);
+    gemm(ly.fc1);
+    gemm(ly.fc2);
+    ln(ly.fc2.k_splits, ly.fc2b, ly.next_g, ly.next_b);
     n += 11;
   }
   if (a.with_logits) {
-    run_gemm_rows(*a.vocab, a.R, a.pdl, s);
+    gemm(*a.vocab);
     ++n;
   }
   return n;

@@ -136,8 +136,9 @@ struct wisb_handle {
   DevBuf<DecState> st;
   DevBuf<int> row_pos, row_slot, max_new_u;
   int search_rows = 0;  // rows the search / state buffers above are sized for
+  int search_gen = 0, bd_search_gen = -1;  // reallocation count of those buffers / the one the batched-pass plans were built for
   // batched decoder pass (more than DEC_MAX_ROWS rows): workspaces for bd_rows (multiple of 128) rows, bd_tcap positions
-  int batch_rows = 320, batch_pdl = 1, decoder_batch = 1, mega_barrier = 0, cross_tc = 1;  // options: row capacity of one shared pass; programmatic dependent launch
+  int batch_rows = 320, batch_pdl = 1, decoder_batch = 1, mega_barrier = 0, cross_tc = 1, debug_chunk = 1;  // options: row capacity of one shared pass; programmatic dependent launch
   int bd_rows = 0, bd_tcap = 0, bd_launches_step = 0;
   DevBuf<float> bx, bq, bpart, blogits;
   DevBuf<__half> bxn, bctx, bh, bkc, bvc;
@@ -335,6 +336,7 @@ void ensure_search(wisb_handle* h, int rows) {
   h->pin_i.ensure(4 + R * (T_MAX + 2));
   h->pin_f.ensure(R * 130);
   h->search_rows = rows;
+  ++h->search_gen;  // whoever baked these pointers into plans must rebuild them
 }
 
 void finish_create(wisb_handle* h) {
@@ -949,7 +951,8 @@ void ensure_batch(wisb_handle* h, int rows, int t_need) {
   int tc = round_up(t_need, 32);
   if (tc > T_MAX) tc = T_MAX;
   ensure_search(h, rows);
-  if (Rp <= h->bd_rows && tc <= h->bd_tcap) return;
+  // (the QKV epilogues hold the row_slot / row_pos pointers of the search state: a reallocation there stales the plans)
+  if (Rp <= h->bd_rows && tc <= h->bd_tcap && h->bd_search_gen == h->search_gen) return;
   if (Rp < h->bd_rows) Rp = h->bd_rows;
   if (tc < h->bd_tcap) tc = h->bd_tcap;
   WISB_CUDA(cudaStreamSynchronize(h->stream));
@@ -963,8 +966,10 @@ void ensure_batch(wisb_handle* h, int rows, int t_need) {
   h->bpart.ensure(8 * M * d, true);
   h->blogits.ensure(M * dm.n_vocab_pad, true);
   const size_t layer_cache = M * tc * d;
-  h->bkc.release();
-  h->bvc.release();
+  if (layer_cache * L > h->bkc.n) {  // (free first: the two caches are the largest buffers of the handle)
+    h->bkc.release();
+    h->bvc.release();
+  }
   h->bkc.ensure(layer_cache * L, true);
   h->bvc.ensure(layer_cache * L, true);
   h->bd_layers.assign(L, BatchLayer());
@@ -1019,6 +1024,7 @@ void ensure_batch(wisb_handle* h, int rows, int t_need) {
   }
   h->bd_rows = Rp;
   h->bd_tcap = tc;
+  h->bd_search_gen = h->search_gen;
 }
 
 BatchArgs make_batch_args(wisb_handle* h, const DecodeCfg& c) {
@@ -1049,6 +1055,13 @@ BatchArgs make_batch_args(wisb_handle* h, const DecodeCfg& c) {
   a.num_sms = h->num_sms;
   a.ckv_map = &h->ckv_map;
   a.ckv_base = h->ckv.p;
+  if (h->profile) {
+    a.prof = [](void* ctx, int cat, int begin) {
+      wisb_handle* hh = static_cast<wisb_handle*>(ctx);
+      if (begin) hh->prof_begin(cat); else hh->prof_end();
+    };
+    a.prof_ctx = h;
+  }
   return a;
 }
 
@@ -1111,7 +1124,7 @@ int decode_batch(wisb_handle* h, const DecodeCfg& c, const int32_t* prompts, con
     SearchArgs sa = make_batch_search_args(h, c);
     search_init_run(sa, h->prompt_dev.p, s, 1);
     DecGraphs* g = nullptr;
-    if (h->use_graphs) {
+    if (h->use_graphs && !h->profile) {  // (the per-kernel timing hook needs eager launches)
       GraphKey key;
       memset(&key, 0, sizeof(key));
       key.n_utt = c.n_utt; key.beam = c.beam; key.prompt_len = c.prompt_len; key.max_new = c.max_new;
@@ -1330,6 +1343,7 @@ int wisb_set_option(wisb_handle* h, const char* key, int value) {
     }
     else if (k == "batch_pdl") h->batch_pdl = value ? 1 : 0;
     else if (k == "mega_barrier") h->mega_barrier = value ? 1 : 0;
+    else if (k == "debug_chunk") h->debug_chunk = value;
     else if (k == "cross_tc") {  // 1: tcgen05 cross-attention in the batched pass, 0: the SIMT cluster kernel (cross-check)
       h->cross_tc = value ? 1 : 0;
       drop_graphs(h);
@@ -1608,21 +1622,26 @@ int wisb_debug_forced_logits(wisb_handle* h, const float* mel, const int32_t* to
     memcpy(h->pin_i.p + 4, tokens, sizeof(int) * n_tokens);
     WISB_CUDA(cudaMemcpyAsync(h->prompt_dev.p, h->pin_i.p + 4, sizeof(int) * n_tokens, cudaMemcpyHostToDevice, s));
     if (h->decoder_batch == 2) {  // the batched pass, one row: position p of the token list per pass
-      ensure_batch(h, 1, n_tokens);
+      ensure_batch(h, MAX_BEAM, n_tokens);
       const size_t head_block = static_cast<size_t>(dm.n_heads) * T_ENC_PAD * HEAD_DIM;
       for (int i = 0; i < dm.n_dec_layers; ++i) {
         h->bd_layers[i].ck = h->ckv.p + static_cast<size_t>(i * 2 + 0) * head_block;
         h->bd_layers[i].cv = h->ckv.p + static_cast<size_t>(i * 2 + 1) * head_block;
       }
-      for (int p = 0; p < n_tokens; ++p) {
-        prefill_rows_run(h->tokens.p, h->row_pos.p, h->row_slot.p, h->prompt_dev.p, n_tokens, 1, p, 1, 1, s);
+      // `debug_chunk` positions per pass (1..8): > 1 feeds consecutive positions as rows of one pass, the way the prompt
+      // prefix is prefilled (exercises the multi-row paths of the attention kernels under teacher forcing)
+      const int chunk_max = h->debug_chunk < 1 ? 1 : (h->debug_chunk > MAX_BEAM ? MAX_BEAM : h->debug_chunk);
+      for (int p = 0; p < n_tokens; p += chunk_max) {
+        const int chunk = n_tokens - p < chunk_max ? n_tokens - p : chunk_max;
+        prefill_rows_run(h->tokens.p, h->row_pos.p, h->row_slot.p, h->prompt_dev.p, n_tokens, 1, p, chunk, 1, s);
         BatchArgs a = make_batch_args(h, c);
-        a.R = 1;
-        a.rows_per_utt = 1;
+        a.R = chunk;
+        a.rows_per_utt = chunk;
         a.prefill = 1;
         a.with_logits = 1;
         batch_pass_run(a, h->bd_layers.data(), dm.n_dec_layers, s);
-        WISB_CUDA(cudaMemcpyAsync(logits_out + static_cast<size_t>(p) * dm.n_vocab, h->blogits.p, sizeof(float) * dm.n_vocab, cudaMemcpyDeviceToHost, s));
+        WISB_CUDA(cudaMemcpy2DAsync(logits_out + static_cast<size_t>(p) * dm.n_vocab, sizeof(float) * dm.n_vocab, h->blogits.p,
+                                    sizeof(float) * dm.n_vocab_pad, sizeof(float) * dm.n_vocab, chunk, cudaMemcpyDeviceToHost, s));
       }
       WISB_CUDA(cudaStreamSynchronize(s));
       return;
