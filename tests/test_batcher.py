@@ -118,3 +118,21 @@ def test_asyncio_face_and_queue_limit():
 
     asyncio.run(main())
     assert len(eng.calls) < 8
+
+
+def test_requests_with_different_max_length_share_one_call():
+    # the engine takes one length limit per window (wisb_generate_ex), so max_length is not part of the compatibility key
+    eng = FakeEngine(delay=0.05)
+    with TranscribeBatcher(eng, max_batch=16, max_wait_ms=30) as b:
+        f1 = b.submit(_window(1, 2), PROMPT, beam_size=5, max_length=30)
+        f2 = b.submit(_window(2, 1), PROMPT, beam_size=5, max_length=72)
+        f3 = b.submit(_window(3, 1), PROMPT, beam_size=5)
+        r1, r2, r3 = f1.result(timeout=5), f2.result(timeout=5), f3.result(timeout=5)
+    assert [r.sequences_ids[0][0] for r in r1 + r2 + r3] == [1, 1, 2, 3]
+    assert len(eng.calls) == 1 and eng.calls[0][0] == 4
+    assert list(eng.calls[0][2]["max_length"]) == [30, 30, 72, 448]
+    # equal limits stay a plain int (the CTranslate2 meaning)
+    eng2 = FakeEngine()
+    with TranscribeBatcher(eng2, max_batch=4, max_wait_ms=10) as b:
+        b.submit(_window(1), PROMPT, beam_size=5, max_length=40).result(timeout=5)
+    assert eng2.calls[0][2]["max_length"] == 40

@@ -2,16 +2,23 @@
 
 The reference serialises requests: ``do_whisper`` is called synchronously on the asyncio event-loop thread of a
 single-worker gunicorn (/root/reference/main.py:1174-1215, 1243-1348; entrypoint.sh:19-21), two windows per engine call
-(``concurrent_gpu_chunks``, main.py:91-94, 676-693).  The B200 engine reads the 1.8 GB of decoder weights once per
-decoder pass whatever the number of rows, so concurrent ``/api/asr`` and ``/api/willow`` requests should share passes.
+(``concurrent_gpu_chunks``, main.py:91-94, 676-693).  The B200 engine decodes every window of a call in ONE shared
+decoder pass per generated token (rows = windows x beams up to the engine's row capacity, 320 by default = 64 windows at
+beam 5; csrc/decoder_batch.cu): the 1.6 GB of decoder weights stream once per pass whatever the number of rows, finished
+windows leave the pass, and requests with different ``max_length`` ride the same pass (per-window limits).  So
+concurrent ``/api/asr`` and ``/api/willow`` requests should be coalesced -- measured on a B200 (large-v2, beam 5): 64
+mixed-length windows in one call decode about 8x faster than one after the other (bench.py ``configs2``).
 This module is the piece a WIS maintainer puts between the endpoints and the engine:
 
     batcher = TranscribeBatcher(whisper_model, max_batch=64, max_wait_ms=2)
     results = await batcher.generate(features, prompt, beam_size=5)      # inside the FastAPI handlers
     results = batcher.submit(features, prompt, beam_size=5).result()      # from plain threads
 
-Requests are compatible when they share the prompt and every generation option (same decoder configuration); a batch is
-closed when ``max_batch`` windows are collected or ``max_wait_ms`` after its oldest request arrived, whichever is first.
+Requests are compatible when they share the prompt and every generation option except ``max_length`` (same decoder
+configuration; the length limits travel per window); a batch is closed when ``max_batch`` windows are collected or
+``max_wait_ms`` after its oldest request arrived, whichever is first.  Latency note: every request of a batch is
+answered when the whole batch has been decoded (the slowest window decides), so ``max_batch`` trades throughput against
+the latency of short requests; ``max_batch`` above the engine's row capacity / beam only adds queueing.
 The engine call runs on the batcher's own thread, so the event loop is never blocked (the C ABI releases the GIL).
 """
 from __future__ import annotations
@@ -28,13 +35,14 @@ from .models import StorageView
 
 
 class _Request:
-    __slots__ = ("features", "n", "key", "prompt", "opts", "future", "t_arrival")
+    __slots__ = ("features", "n", "key", "prompt", "opts", "max_length", "future", "t_arrival")
 
     def __init__(self, features, prompt, opts):
         self.features = features
         self.n = int(features.shape[0])
         self.prompt = list(prompt)
         self.opts = dict(opts)
+        self.max_length = int(self.opts.pop("max_length", 448))  # per request; merged per window by the worker
         self.key = (tuple(self.prompt), tuple(sorted((k, _freeze(v)) for k, v in self.opts.items())))
         self.future = Future()
         self.t_arrival = time.monotonic()
@@ -146,7 +154,9 @@ class TranscribeBatcher:
             n = sum(r.n for r in live)
             try:
                 feats = live[0].features if len(live) == 1 else np.concatenate([r.features for r in live], axis=0)
-                out = self._model.generate(StorageView.from_array(feats), [live[0].prompt] * n, **live[0].opts)
+                limits = [r.max_length for r in live for _ in range(r.n)]
+                ml = limits[0] if len(set(limits)) == 1 else np.asarray(limits, np.int32)
+                out = self._model.generate(StorageView.from_array(feats), [live[0].prompt] * n, max_length=ml, **live[0].opts)
                 if len(out) != n:
                     raise RuntimeError(f"engine returned {len(out)} results for {n} windows")
             except BaseException as e:  # noqa: BLE001 -- every waiter must learn about it

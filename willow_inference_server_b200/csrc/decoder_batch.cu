@@ -367,7 +367,8 @@ constexpr int XT_Q_BYTES = XT_NQ * HEAD_DIM * 2;   // 2 KB
 constexpr int XT_OFF_P = XT_STAGES * XT_TILE;
 constexpr int XT_OFF_Q = XT_OFF_P + XT_NT * XT_P_TILE;
 constexpr int XT_OFF_BAR = XT_OFF_Q + 2 * XT_Q_BYTES;
-constexpr int XT_SMEM = XT_OFF_BAR + 1024 + 1024;  // + barriers / scratch (720 B) + alignment slack
+constexpr int XT_MAX_UTT = 512;                    // utterances of one pass (row capacity <= 1024, >= 2 ... rows each, or greedy)
+constexpr int XT_SMEM = XT_OFF_BAR + 2048 + 1024;  // + barriers / scratch / live list (1748 B) + alignment slack
 constexpr int XT_D2_COL = XT_NT * XT_NQ;           // 192: O^T accumulator columns
 constexpr float XT_LOG2E = 1.4426950408889634f;
 
@@ -422,24 +423,42 @@ bd_cross_attn_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const float*
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // q and the `done` flags come from the previous kernels of the chain
 
-  const int n_items = n_utt * H;
-  auto item_live = [&](int item) { return done == nullptr || done[item / H] == 0; };
+  // live utterances, compacted: item k of this CTA is (s_live[idx / H], idx % H) with idx = blockIdx.x + k * gridDim.x, so the
+  // CTAs stay balanced whichever utterances have finished
+  unsigned short* s_live = reinterpret_cast<unsigned short*>(s_red + 128);
+  int* s_nlive = reinterpret_cast<int*>(s_live + XT_MAX_UTT);
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int u = 0; u < n_utt; ++u)
+      if (done == nullptr || done[u] == 0) s_live[n++] = static_cast<unsigned short>(u);
+    *s_nlive = n;
+  }
+  __syncthreads();
+  const int n_idx = *s_nlive * H;
+  const int n_my = (static_cast<int>(blockIdx.x) < n_idx) ? (n_idx - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+  auto item_of = [&](int k) {  // -> u * H + h of this CTA's k-th item
+    const int idx = blockIdx.x + k * gridDim.x;
+    return static_cast<int>(s_live[idx / H]) * H + idx % H;
+  };
 
+  // Unit order through the ring: K(0); then per item i: K(i+1), V(i).  The keys of the NEXT item stream (and their S^T MMAs
+  // run) while the softmax of item i is busy, so the TMA stream never waits for the softmax.
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer: K tiles, then V tiles of every item
+    // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       unsigned unit = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        if (!item_live(item)) continue;
-        for (int kv = 0; kv < 2; ++kv) {
-          const long long row0 = (kv == 0 ? row_k0 : row_v0) + static_cast<long long>(item) * T_ENC_PAD;
-          for (int j = 0; j < XT_NT; ++j, ++unit) {
-            const int st = unit % XT_STAGES;
-            mbar_wait(empty_bar(st), ((unit / XT_STAGES) & 1u) ^ 1u);
-            mbar_arrive_expect_tx(full_bar(st), XT_TILE);
-            tma_load_2d(base + st * XT_TILE, &map_kv, full_bar(st), 0, static_cast<int>(row0 + j * 128));
-          }
+      auto load12 = [&](long long row0) {
+        for (int j = 0; j < XT_NT; ++j, ++unit) {
+          const int st = unit % XT_STAGES;
+          mbar_wait(empty_bar(st), ((unit / XT_STAGES) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(full_bar(st), XT_TILE);
+          tma_load_2d(base + st * XT_TILE, &map_kv, full_bar(st), 0, static_cast<int>(row0 + j * 128));
         }
+      };
+      if (n_my > 0) load12(row_k0 + static_cast<long long>(item_of(0)) * T_ENC_PAD);
+      for (int k = 0; k < n_my; ++k) {
+        if (k + 1 < n_my) load12(row_k0 + static_cast<long long>(item_of(k + 1)) * T_ENC_PAD);
+        load12(row_v0 + static_cast<long long>(item_of(k)) * T_ENC_PAD);
       }
     }
   } else if (warp == 1) {
@@ -448,9 +467,7 @@ bd_cross_attn_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const float*
       constexpr uint32_t idesc_s = make_idesc_f16(128, XT_NQ, false, false);
       constexpr uint32_t idesc_o = make_idesc_f16(64, XT_NQ, true, false);  // A = V tile, MN-major (head dim contiguous)
       unsigned unit = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        if (!item_live(item)) continue;
+      auto mma_scores = [&](int it) {  // S^T of item `it` -> D1
         mbar_wait(q_full0 + 8u * (it & 1), (it >> 1) & 1u);
         if (it > 0) mbar_wait(d1_empty, (it - 1) & 1u);
         tc_fence_after();
@@ -467,6 +484,10 @@ bd_cross_attn_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const float*
           umma_commit(empty_bar(st));
         }
         umma_commit(s_full);
+      };
+      if (n_my > 0) mma_scores(0);
+      for (int it = 0; it < n_my; ++it) {
+        if (it + 1 < n_my) mma_scores(it + 1);
         mbar_wait(p_full, it & 1u);
         if (it > 0) mbar_wait(d2_empty, (it - 1) & 1u);
         tc_fence_after();
@@ -483,7 +504,6 @@ bd_cross_attn_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const float*
           umma_commit(empty_bar(st));
         }
         umma_commit(o_full);
-        ++it;
       }
     }
   } else {
@@ -511,18 +531,12 @@ bd_cross_attn_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const float*
       __syncwarp();
       if (lane == 0) mbar_arrive(q_full0 + 8u * buf);
     };
-    auto next_live = [&](int item) {
-      item += gridDim.x;
-      while (item < n_items && !item_live(item)) item += gridDim.x;
-      return item;
-    };
-    int item = blockIdx.x;
-    while (item < n_items && !item_live(item)) item += gridDim.x;
-    if (item < n_items) write_q(item, 0);
-    int it = 0;
-    for (; item < n_items; ++it) {
-      const int nxt = next_live(item);
-      if (nxt < n_items) write_q(nxt, (it + 1) & 1);  // that buffer's last reader (MMA1 of item it-1) is done
+    if (n_my > 0) write_q(item_of(0), 0);
+    for (int it = 0; it < n_my; ++it) {
+      const int item = item_of(it);
+      // Q of the next item (its S^T MMAs are issued while this item's softmax runs); that buffer's last reader, MMA1 of
+      // item it - 1, completed before s_full(it - 1)
+      if (it + 1 < n_my) write_q(item_of(it + 1), (it + 1) & 1);
       mbar_wait(s_full, it & 1u);
       tc_fence_after();
       float sc[XT_NT][NB];
@@ -605,7 +619,6 @@ bd_cross_attn_tc_kernel(const __grid_constant__ CUtensorMap map_kv, const float*
           }
         }
       }
-      item = nxt;
     }
   }
   tc_fence_before();
@@ -632,6 +645,7 @@ int bd_ca_smem(int nb) { return 2 * BD_CA_KEYS * HEAD_DIM * 2 + BD_CA_GROUPS * n
 
 template <int NB>
 void cross_tc_launch(const BatchArgs& a, const BatchLayer& ly, cudaStream_t s) {
+  WISB_REQUIRE(a.n_utt <= XT_MAX_UTT, "cross-attention: more than 512 utterances in one pass");
   static std::atomic<unsigned long long> once{0};
   once_per_device(once, [] {
     WISB_CUDA(cudaFuncSetAttribute(bd_cross_attn_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, XT_SMEM));

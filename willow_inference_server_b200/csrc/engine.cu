@@ -138,7 +138,7 @@ struct wisb_handle {
   int search_rows = 0;  // rows the search / state buffers above are sized for
   int search_gen = 0, bd_search_gen = -1;  // reallocation count of those buffers / the one the batched-pass plans were built for
   // batched decoder pass (more than DEC_MAX_ROWS rows): workspaces for bd_rows (multiple of 128) rows, bd_tcap positions
-  int batch_rows = 320, batch_pdl = 1, decoder_batch = 1, mega_barrier = 0, cross_tc = 1, debug_chunk = 1;  // options: row capacity of one shared pass; programmatic dependent launch
+  int batch_rows = 320, batch_pdl = 1, decoder_batch = 1, mega_barrier = 1, cross_tc = 1, debug_chunk = 1;  // options: row capacity of one shared pass; programmatic dependent launch
   int bd_rows = 0, bd_tcap = 0, bd_launches_step = 0;
   DevBuf<float> bx, bq, bpart, blogits;
   DevBuf<__half> bxn, bctx, bh, bkc, bvc;
