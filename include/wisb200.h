@@ -90,6 +90,11 @@ int wisb_set_option(wisb_handle* h, const char* key, int value);
 /* ---- diagnostics used by tests/ (run the product kernels on caller data) ---- */
 /* C[M,N] (float32) = A[M,K] . W[N,K]^T with fp16 inputs given as raw uint16; impl 0 = tcgen05 kernel, 1 = SIMT check */
 int wisb_debug_gemm(wisb_handle* h, const uint16_t* a, const uint16_t* w, float* c, int M, int N, int K, int impl, int bn);
+/* the tcgen05 skinny-GEMV building block of the decoder pass on caller data: out[R,N] (float32) = x[R,K] (float32, rounded
+ * to fp16 inside) . W[N,K]^T (fp16 as raw uint16) + bias (may be NULL); R <= 8, K % 64 == 0, K <= 5120.  avg_us (may be
+ * NULL) receives the average kernel time over `iters` back-to-back launches. */
+int wisb_debug_gemv_tc(wisb_handle* h, const float* x, const uint16_t* w, const float* bias, float* out, int R, int N, int K,
+                       int iters, float* avg_us);
 /* per-phase %globaltimer stamps of the last persistent decoder pass (option "mega_trace" = 1): n <= 2048 values */
 int wisb_debug_read_trace(wisb_handle* h, unsigned long long* out, int n);
 /* encoder output after the final LayerNorm, float32 [B,1500,d_model]; n_layers < 0 = all */

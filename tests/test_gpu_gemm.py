@@ -65,3 +65,19 @@ def test_gemm_rejects_bad_shapes(h):
         h.debug_gemm(np.zeros((100, 64), np.float16), np.zeros((128, 64), np.float16))
     with pytest.raises(ValueError):
         h.debug_gemm(np.zeros((128, 60), np.float16), np.zeros((128, 60), np.float16))
+
+
+@pytest.mark.parametrize("R,N,K", [(5, 3840, 1280), (8, 1280, 5120), (1, 1280, 1280), (5, 5120, 1280), (3, 10240, 256), (5, 384, 384)])
+def test_gemv_tc_matches_fp32_reference(h, R, N, K):
+    # the tcgen05 skinny GEMV (weight rows on the MMA's M, activation rows on its N): x is rounded to fp16 inside, so the
+    # reference multiplies the fp16-rounded x by the fp16 weights in fp32
+    rng = np.random.default_rng(R * 1000 + N + K)
+    x = rng.standard_normal((R, K)).astype(np.float32) * 3.0
+    w = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float16)
+    bias = rng.standard_normal(N).astype(np.float32)
+    got, _ = h.debug_gemv_tc(x, w, bias)
+    want = x.astype(np.float16).astype(np.float32) @ w.astype(np.float32).T + bias
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 2e-3
+    got2, _ = h.debug_gemv_tc(x, w, None)
+    assert np.abs(got2 - (want - bias)).max() <= 2e-3

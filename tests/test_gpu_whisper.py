@@ -92,18 +92,31 @@ def test_graphs_and_eager_agree(pair):
 
 
 def test_persistent_pass_kernel_vs_per_op_chain(pair):
-    # the persistent decoder-pass kernel and the per-op kernel chain are two implementations of the same arithmetic
+    # three implementations of the same decoder arithmetic for <= 8 rows: the persistent pass with its GEMV phases on
+    # tcgen05 (default; fp16 B operand), the persistent SIMT pass (fp32 activations) and the per-op kernel chain
     dims, oracle, h = pair
     mel = mel_inputs(4)[:2]
     toks = PROMPT + [100, 2000, 30000, 41000, 12]
+    want = oracle.forced_logits(oracle.encode(mel[:1])[0], toks).numpy()
     a = h.debug_forced_logits(mel[:1], toks)
     ids_a, _ = h.generate(mel, [PROMPT] * 2, beam_size=5)
-    h.set_option("decoder_mega", 0)
-    b = h.debug_forced_logits(mel[:1], toks)
-    ids_b, _ = h.generate(mel, [PROMPT] * 2, beam_size=5)
-    h.set_option("decoder_mega", 1)
-    assert np.abs(a - b).max() < 2e-3
-    assert ids_a == ids_b
+    h.set_option("mega_tc", 0)
+    try:
+        s_ = h.debug_forced_logits(mel[:1], toks)
+        ids_s, _ = h.generate(mel, [PROMPT] * 2, beam_size=5)
+        h.set_option("decoder_mega", 0)
+        b = h.debug_forced_logits(mel[:1], toks)
+        ids_b, _ = h.generate(mel, [PROMPT] * 2, beam_size=5)
+    finally:
+        h.set_option("decoder_mega", 1)
+        h.set_option("mega_tc", 1)
+    assert np.abs(s_ - b).max() < 2e-3            # SIMT pass vs chain: same fp32 arithmetic, different summation order
+    assert np.abs(a - want).max() <= LOGIT_TOL     # tensor-core pass vs the oracle
+    assert np.abs(a - s_).max() <= LOGIT_TOL
+    assert ids_s == ids_b
+    res, robust = robust_cases(oracle, mel, [PROMPT] * 2, 5)
+    for i in robust:
+        assert ids_a[i] == ids_s[i] == res[i].sequences_ids[0], i
 
 
 def test_max_length_and_suppress(pair):

@@ -137,5 +137,10 @@ def test_transcribe_long_orchestration(monkeypatch):
     calls.clear()
     out = audio.transcribe_long(Engine(), np.zeros(800000, np.float32), [50258], Tok(), max_windows_per_call=2)
     assert out.tolist() == list(range(1, 12)) and [c[0] for c in calls] == [2, 1]
-    monkeypatch.setattr(audio, "log_mel_chunks", lambda a, handle=None: (fake_chunks(a)[0][:1], fake_chunks(a)[1][:1]))
-    assert audio.transcribe_long(Engine(), np.zeros(10, np.float32), [50258], Tok()).tolist() == [1, 2, 3, 4, 5, 6]
+    # <= 30 s: ONE zero-padded window and no windowing at all, as the reference does (main.py:587-617) -- 25 s of audio
+    # would otherwise become two 22-s windows plus a stitch
+    calls.clear()
+    monkeypatch.setattr(audio, "log_mel_window", lambda a, handle=None: fake_chunks(a)[0][:1])
+    monkeypatch.setattr(audio, "log_mel_chunks", lambda a, handle=None: (_ for _ in ()).throw(AssertionError("windowed a short utterance")))
+    assert audio.transcribe_long(Engine(), np.zeros(400000, np.float32), [50258], Tok()).tolist() == [1, 2, 3, 4, 5, 6]
+    assert [c[0] for c in calls] == [1]

@@ -38,6 +38,8 @@ _SIGS = {
     "wisb_get_timing": (C.c_int, [C.c_void_p, C.c_void_p]),
     "wisb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "wisb_debug_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "wisb_debug_gemv_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p]),
     "wisb_debug_read_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "wisb_debug_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "wisb_debug_forced_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
@@ -205,6 +207,18 @@ class Handle:
         c = np.zeros((M, N), np.float32)
         check(lib().wisb_debug_gemm(self._h, ptr(a16), ptr(w16), ptr(c), M, N, K, impl, bn))
         return c
+
+    def debug_gemv_tc(self, x: np.ndarray, w16: np.ndarray, bias=None, iters: int = 0):
+        """tcgen05 skinny GEMV on caller data -> (out float32 [R, N], average kernel time in us over `iters` launches)."""
+        x = np.ascontiguousarray(x, np.float32)
+        w16 = np.ascontiguousarray(w16, np.float16)
+        R, K = x.shape
+        N = w16.shape[0]
+        out = np.zeros((R, N), np.float32)
+        us = C.c_float(0.0)
+        b = None if bias is None else np.ascontiguousarray(bias, np.float32)
+        check(lib().wisb_debug_gemv_tc(self._h, ptr(x), ptr(w16), ptr(b), ptr(out), R, N, K, int(iters), C.byref(us)))
+        return out, float(us.value)
 
     def debug_read_trace(self, n: int = 600) -> np.ndarray:
         out = np.zeros(n, np.uint64)

@@ -148,6 +148,16 @@ def log_mel_chunks(audio, handle=None):
     return (handle or _get_frontend()).logmel(np.ascontiguousarray(pcm), offs, lens), strides
 
 
+def log_mel_window(audio, handle=None):
+    """One utterance of at most 30 s -> float32 [1, 80, 3000] (zero padding to the window fused in the kernel): what
+    ``log_mel_spectrogram(pad_or_trim(audio)).numpy()[None]`` yields in main.py:612-617."""
+    pcm = np.asarray(audio)
+    if pcm.dtype not in (np.float32, np.int16):
+        pcm = pcm.astype(np.float32)
+    n = min(int(pcm.shape[0]), N_SAMPLES)
+    return (handle or _get_frontend()).logmel(np.ascontiguousarray(pcm[:n]), [0], [n])
+
+
 def transcribe_long(model, audio, prompt, tokenizer, *, beam_size: int = 5, batcher=None, max_windows_per_call: int = 64,
                     **generate_options):
     """The long-audio path of ``do_whisper`` (main.py:582-617, 676-714) on top of the pieces above: window the
@@ -160,9 +170,7 @@ def transcribe_long(model, audio, prompt, tokenizer, *, beam_size: int = 5, batc
     pcm = np.asarray(audio)
     if pcm.ndim == 1 and pcm.shape[0] <= N_SAMPLES:
         # <= 30 s: the reference does not window at all (main.py:587-617), it decodes one zero-padded 30-s window
-        if pcm.dtype not in (np.float32, np.int16):
-            pcm = pcm.astype(np.float32)
-        mel = _get_frontend().logmel(np.ascontiguousarray(pcm), [0], [pcm.shape[0]])
+        mel = log_mel_window(pcm)
         strides = [(pcm.shape[0], 0, 0)]
     else:
         mel, strides = log_mel_chunks(audio)

@@ -151,6 +151,10 @@ struct MegaGemv {
   float* out = nullptr;
   long long ldo = 0;
   int N = 0, K = 0, epi = GV_STORE;
+  // tensor-core pass (dec_pass_tc_kernel): 2-D tensor map over the row-major W [N, K] (box = 64 k x rows_box weight rows,
+  // 128-byte swizzle; device memory, 64-byte aligned), weight rows per box, k-blocks per ring unit
+  const CUtensorMap* tmap = nullptr;
+  int rows_box = 0, kbu = 0;
 };
 struct MegaLayer {
   MegaGemv qkv, o, cq, co, fc1, fc2;
@@ -183,6 +187,7 @@ struct MegaArgs {
   unsigned* flags = nullptr;     // grid-barrier epoch flags, one 128-byte line per CTA
   unsigned* epoch_base = nullptr;
   int barrier_mode = 0;          // 0: per-CTA epoch flags, 1: shared counter (red.release + spin)
+  int tc = 0;                    // 1: GEMV phases on tcgen05 (dec_pass_tc_kernel)
   unsigned long long* trace = nullptr;  // optional: [2*k] = time phase k starts, [2*k+1] = time CTA 0 reached barrier k
 };
 size_t mega_flags_words();
@@ -192,6 +197,10 @@ void mega_chunk_major(const __half* src, __half* dst, int N, int K, cudaStream_t
 void mega_ln_fold(const __half* w, const float* g, const float* b, const float* bias, float* s2, float* biasf, int N, int K,
                   cudaStream_t stream);
 void dec_pass_run(const MegaArgs& a, int num_sms, cudaStream_t stream);
+
+// tcgen05 skinny GEMV (gemv_tc.cu), diagnostics entry: returns the average kernel time in microseconds
+float gemv_tc_debug_run(const float* x, const __half* w, const float* bias, float* out, int R, int N, int K, int num_sms,
+                        int iters, cudaStream_t stream);
 
 // language detection head: softmax over lang ids of the logits of row u*beam (one step on <|startoftranscript|>)
 void lang_probs_run(const float* logits, long long ldl, const int* lang_ids, int n_lang, int n_utt, int row_stride,

@@ -37,11 +37,12 @@ constexpr int MG_NSTAGE = 2;
 constexpr int MG_CA_KEYS_MAX = MG_STAGE_BYTES / 128;    // 288 keys per K (or V) chunk
 constexpr int MG_SCRATCH = 29696;                       // self-attention V rows + probabilities / cross-attention merge
 constexpr int MG_SLOT_BYTES = MG_CONS_WARPS * 448 * 2;  // per-warp cache-slot table of the warp's self-attention task
-constexpr int MG_LY_BYTES = 2 * 512;                    // double-buffered copy of the layer descriptor
+constexpr int MG_LY_STRIDE = 640;
+constexpr int MG_LY_BYTES = 2 * MG_LY_STRIDE;           // double-buffered copy of the layer descriptor
 constexpr int MG_RED_FLOATS = (2 * 2 + 1) * MG_CONS_WARPS * 32;  // 2 buffers x 2 sets + LN partials
 constexpr int MG_SMEM = MG_NSTAGE * MG_STAGE_BYTES + 1024 + MG_RED_FLOATS * 4 + 4224 + MG_SCRATCH + MG_SLOT_BYTES + MG_LY_BYTES;
 static_assert(MG_SMEM <= 232448, "decoder pass: shared memory");
-static_assert(sizeof(MegaLayer) % 16 == 0 && sizeof(MegaLayer) <= 512, "layer descriptor is copied with 16-byte cp.async");
+static_assert(sizeof(MegaLayer) % 16 == 0 && sizeof(MegaLayer) <= MG_LY_STRIDE, "layer descriptor is copied with 16-byte cp.async");
 // columns a thread accumulates per unit: the transposing reduction handles GP * NR <= 32 values
 __host__ __device__ constexpr int mg_gp(int nr) { return 32 / nr < 6 ? 32 / nr : 6; }
 // accumulator sets per thread: 2 x 6 columns for <= 5 rows (the stage holds 12 weight-row chunks), 1 x 4 for 8 rows
@@ -548,7 +549,9 @@ __device__ __noinline__ void consume_self_attn(const MegaArgs& A, const MegaLaye
 // 28 groups of 8 lanes walk the split's keys with an online softmax for all beams at once (K/V are read once for every
 // beam); groups are merged by shuffles (4 per warp) and shared memory into one partial (acc[64], m, l) per beam; the
 // last split of a head to arrive (atomic counter) merges the S partials into ctx.
-template <int NB>
+// kOneArrive: the ring's empty barriers count ONE arrival per stage (tensor-core pass: tcgen05.commit releases the weight
+// stages) instead of one per consumer warp
+template <int NB, bool kOneArrive = false>
 __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid, float* s_part, unsigned tag) {
   const int grp = ctid >> 3, gl = ctid & 7;
   constexpr int NGRP = MG_CONS / 8;  // 28
@@ -650,7 +653,7 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
     }
     trace_ev(A, ctid, s_tr, 13);
     __syncwarp();
-    if ((ctid & 31) == 0) {
+    if (!kOneArrive && (ctid & 31) == 0) {
       mbar_arrive(ring_empty0 + 8u * stK);
       mbar_arrive(ring_empty0 + 8u * stV);
     }
@@ -685,6 +688,10 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
     }
     trace_ev(A, ctid, s_tr, 14);
     cons_sync();
+    if (kOneArrive && ctid == 0) {  // every warp has left the K / V stages
+      mbar_arrive(ring_empty0 + 8u * stK);
+      mbar_arrive(ring_empty0 + 8u * stV);
+    }
     for (int idx = ctid; idx < beam * HEAD_DIM; idx += MG_CONS) {
       const int k = idx / HEAD_DIM, e = idx - k * HEAD_DIM;
       float mm = -INFINITY;
@@ -805,7 +812,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs 
   // layer descriptors travel to shared memory one layer ahead (cp.async), so no phase starts with a global round trip
   auto prefetch_layer = [&](int l) {
     if (ctid < static_cast<int>(sizeof(MegaLayer) / 16))
-      cp_async16(smem_u32(reinterpret_cast<uint8_t*>(s_ly) + (l & 1) * 512) + ctid * 16,
+      cp_async16(smem_u32(reinterpret_cast<uint8_t*>(s_ly) + (l & 1) * MG_LY_STRIDE) + ctid * 16,
                  reinterpret_cast<const uint8_t*>(A.layers + l) + ctid * 16);
   };
   if (L > 0) prefetch_layer(0);
@@ -835,7 +842,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs 
   }
   grid_barrier(A, epoch, ctid, epoch0);
   for (int l = 0; l < L; ++l) {
-    const MegaLayer& ly = *reinterpret_cast<const MegaLayer*>(reinterpret_cast<const uint8_t*>(s_ly) + (l & 1) * 512);
+    const MegaLayer& ly = *reinterpret_cast<const MegaLayer*>(reinterpret_cast<const uint8_t*>(s_ly) + (l & 1) * MG_LY_STRIDE);
     if (l + 1 < L) prefetch_layer(l + 1);  // the other buffer was last read in layer l - 1
     consume_gemv<NR>(rg, A, ly.qkv, &ly, ctid, s_red, s_stat);
     grid_barrier(A, epoch, ctid, epoch0);
@@ -862,6 +869,329 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs 
     *A.epoch_base = epoch;
     A.epoch_base[8] = epoch * gridDim.x;  // keeps the counter of the atomic barrier mode in step whatever mode ran
   }
+}
+
+
+// =====================================================================================================================
+// Tensor-core variant of the pass: the six GEMV phases of a layer and the vocabulary projection run on tcgen05
+// (swap-AB skinny GEMV, see gemv_tc.cu): the CTA's weight rows are the MMA's M (64, of which the CTA owns <= 40; the
+// vocabulary slice is walked in groups of 64), the <= 8 activation rows its N.  What disappears against the SIMT pass:
+// the fp32 FMA loop over the weight stage, the transposing shuffle reductions and the shared-memory hop of every phase.
+// What stays: the producer thread and its static weight schedule (now 2-D TMA boxes straight from the row-major W), the
+// grid barrier between phases, the attention phases, LayerNorm folded into the epilogue, residual columns owned by the CTA.
+// Activations are rounded to fp16 when they become the B operand (the encoder and the batched pass do the same).
+// =====================================================================================================================
+constexpr int MT_B_BYTES = 80 * 1024;   // B operand: K / 64 k-blocks x [8 rows x 128 B]  (K <= 5120)
+constexpr int MT_OFF_B = MG_NSTAGE * MG_STAGE_BYTES;  // (the MMA's 64-row read may run up to 8 KB past a stage: into B, harmless)
+constexpr int MT_OFF_BARS = MT_OFF_B + MT_B_BYTES;
+constexpr int MT_SMEM = MT_OFF_BARS + 1024 + MG_RED_FLOATS * 4 + 4224 + MG_SCRATCH + MG_SLOT_BYTES + MG_LY_BYTES + 1024;
+static_assert(MT_SMEM <= 232448, "tensor-core decoder pass: shared memory");
+
+__device__ __noinline__ void produce_gemv_tc(Ring& rg, const MegaGemv& g) {
+  int lo, hi;
+  cta_cols(g.N, lo, hi);
+  const int n_groups = (hi - lo + 63) / 64;
+  const int kblocks = g.K / 64;
+  const int units = (kblocks + g.kbu - 1) / g.kbu;
+  const uint64_t pol = l2_policy_evict_first();
+  for (int gi = 0; gi < n_groups; ++gi) {
+    const int row0 = lo + gi * 64;
+    for (int u = 0; u < units; ++u) {
+      const int kb0 = u * g.kbu, nkb = min(g.kbu, kblocks - kb0);
+      const int st = rg.unit % MG_NSTAGE;
+      mbar_wait(rg.empty(st), ((rg.unit / MG_NSTAGE) & 1u) ^ 1u);
+      mbar_arrive_expect_tx(rg.full(st), static_cast<uint32_t>(nkb * g.rows_box * 128));
+      for (int i = 0; i < nkb; ++i)
+        tma_load_2d_hint(rg.data0 + st * MG_STAGE_BYTES + i * g.rows_box * 128, g.tmap, rg.full(st), (kb0 + i) * 64, row0, pol);
+      ++rg.unit;
+    }
+  }
+}
+
+template <int NR>
+__device__ __noinline__ void consume_gemv_tc(Ring& rg, const MegaArgs& A, const MegaGemv& g_mem, const MegaLayer* ly, int ctid,
+                                            uint8_t* s_b, float* s_lnred, float* s_xown, uint32_t tmem_base, uint32_t d_full,
+                                            unsigned& d_count) {
+  const MegaGemv g = g_mem;
+  const int lane = ctid & 31, warp = ctid >> 5;
+  const int R = A.R;
+  int lo, hi;
+  cta_cols(g.N, lo, hi);
+  const int n_groups = (hi - lo + 63) / 64;
+  const int kblocks = g.K / 64;
+  const int units = (kblocks + g.kbu - 1) / g.kbu;
+  const bool ln = g.ln_s2 != nullptr;
+  // ---- B operand: x (times the LayerNorm gain) -> fp16, [k-block][8 rows][128 B], 16-byte chunks XOR-swizzled by the row;
+  //      the LayerNorm statistics (single pass, fp32) ride along
+  float sx[NR], sxx[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) sx[r] = sxx[r] = 0.f;
+  for (int v = ctid; v < g.K / 8; v += MG_CONS) {
+    const int kb = v >> 3, c = v & 7;
+    float gg[8];
+    if (ln) {
+      const float4 g0v = __ldg(reinterpret_cast<const float4*>(g.ln_g + v * 8)), g1v = __ldg(reinterpret_cast<const float4*>(g.ln_g + v * 8 + 4));
+      gg[0] = g0v.x; gg[1] = g0v.y; gg[2] = g0v.z; gg[3] = g0v.w; gg[4] = g1v.x; gg[5] = g1v.y; gg[6] = g1v.z; gg[7] = g1v.w;
+    }
+    float4 x0[NR], x1[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+      if (r < R) {
+        x0[r] = ldcg_f4(g.x + static_cast<long long>(r) * g.K + v * 8);
+        x1[r] = ldcg_f4(g.x + static_cast<long long>(r) * g.K + v * 8 + 4);
+      }
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+      if (r < R) {
+        float xv[8] = {x0[r].x, x0[r].y, x0[r].z, x0[r].w, x1[r].x, x1[r].y, x1[r].z, x1[r].w};
+        if (ln) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            sx[r] += xv[i];
+            sxx[r] = fmaf(xv[i], xv[i], sxx[r]);
+            xv[i] *= gg[i];
+          }
+        }
+        __half2 h0 = __floats2half2_rn(xv[0], xv[1]), h1 = __floats2half2_rn(xv[2], xv[3]);
+        __half2 h2 = __floats2half2_rn(xv[4], xv[5]), h3 = __floats2half2_rn(xv[6], xv[7]);
+        uint4 u4;
+        u4.x = *reinterpret_cast<uint32_t*>(&h0); u4.y = *reinterpret_cast<uint32_t*>(&h1);
+        u4.z = *reinterpret_cast<uint32_t*>(&h2); u4.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(s_b + kb * 1024 + r * 128 + ((c ^ r) << 4)) = u4;
+      }
+  }
+  if (ln) {
+    float red[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) red[i] = 0.f;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      red[r] = sx[r];
+      red[16 + r] = sxx[r];
+    }
+    s_lnred[warp * 32 + lane] = warp_transpose_reduce32(red, lane);
+  }
+  fence_proxy_async_smem();
+  cons_sync();
+  // ---- one thread issues every MMA of the phase (4 per k-block), each ring unit is released by tcgen05.commit
+  if (ctid == 0) {
+    constexpr uint32_t idesc = make_idesc_f16(64, 8, false, false);
+    const uint32_t sb = smem_u32(s_b);
+    unsigned unit = rg.unit;
+    tc_fence_after();
+    for (int gi = 0; gi < n_groups; ++gi) {
+      for (int u = 0; u < units; ++u, ++unit) {
+        const int kb0 = u * g.kbu, nkb = min(g.kbu, kblocks - kb0);
+        const int st = unit % MG_NSTAGE;
+        mbar_wait(rg.full(st), (unit / MG_NSTAGE) & 1u);
+        tc_fence_after();
+        for (int i = 0; i < nkb; ++i) {
+          const uint64_t da = make_desc_sw128(rg.data0 + st * MG_STAGE_BYTES + i * g.rows_box * 128, 1024);
+          const uint64_t db = make_desc_sw128(sb + (kb0 + i) * 1024, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tmem_base + static_cast<uint32_t>(gi * 8), da + 2u * k, db + 2u * k, idesc, ((kb0 + i) | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(rg.empty(st));
+      }
+    }
+    umma_commit(d_full);
+  }
+  rg.unit += static_cast<unsigned>(n_groups * units);
+  __syncwarp();
+  mbar_wait(d_full, d_count & 1u);
+  ++d_count;
+  tc_fence_after();
+  // ---- epilogue: accumulator row j of a group sits on lane 32 (j / 16) + j % 16 (M = 64): warps 0..3, lanes 0..15
+  if (warp < 4) {
+    float mean[NR], rstd[NR];
+    if (ln) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        float t1 = 0.f, t2 = 0.f;
+        for (int w = 0; w < MG_CONS_WARPS; ++w) {
+          t1 += s_lnred[w * 32 + r];
+          t2 += s_lnred[w * 32 + 16 + r];
+        }
+        mean[r] = t1 / g.K;
+        rstd[r] = rsqrtf(fmaxf(t2 / g.K - mean[r] * mean[r], 0.f) + 1e-5f);
+      }
+    }
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    for (int gi = 0; gi < n_groups; ++gi) {
+      uint32_t acc[8];
+      tmem_ld_32x32b_x8(tmem_base + lane_off + static_cast<uint32_t>(gi * 8), acc);
+      tmem_ld_wait();
+      const int n = lo + gi * 64 + warp * 16 + lane;
+      if (lane < 16 && n < hi) {
+        const float bias = g.bias != nullptr ? __ldg(g.bias + n) : 0.f;
+        const float s2 = ln ? __ldg(g.ln_s2 + n) : 0.f;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          if (r < R) {
+            float v = __uint_as_float(acc[r]);
+            if (ln) v = rstd[r] * (v - mean[r] * s2);
+            v += bias;
+            switch (g.epi) {
+              case GV_STORE:
+                g.out[static_cast<long long>(r) * g.ldo + n] = v;
+                break;
+              case GV_RESID: {
+                const float nv = s_xown[r * 16 + (n - lo)] + v;
+                s_xown[r * 16 + (n - lo)] = nv;
+                g.out[static_cast<long long>(r) * g.ldo + n] = nv;
+                break;
+              }
+              case GV_GELU:
+                g.out[static_cast<long long>(r) * g.ldo + n] = gelu_erf(v);
+                break;
+              case GV_QKV: {
+                const int d = A.d;
+                if (n < d) {
+                  g.out[static_cast<long long>(r) * g.ldo + n] = v;
+                } else {
+                  const int pos = row_pos(A, r);
+                  __half* cache = (n < 2 * d) ? ly->kcache : ly->vcache;
+                  const int e = (n < 2 * d) ? n - d : n - 2 * d;
+                  cache[(static_cast<long long>(row_slot(A, r)) * A.t_max + pos) * d + e] = __float2half_rn(v);
+                }
+                break;
+              }
+              default:
+                break;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+}
+
+template <int NR>
+__global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_tc_kernel(const MegaArgs A) {
+  extern __shared__ __align__(1024) uint8_t mg_smem[];
+  uint8_t* ring_data = mg_smem;
+  uint8_t* s_b = mg_smem + MT_OFF_B;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mg_smem + MT_OFF_BARS);
+  float* s_red = reinterpret_cast<float*>(mg_smem + MT_OFF_BARS + 1024);
+  float* s_stat = s_red + MG_RED_FLOATS;
+  float* s_part = s_stat + 1056;
+  unsigned short* s_slot_tab = reinterpret_cast<unsigned short*>(reinterpret_cast<uint8_t*>(s_part) + MG_SCRATCH);
+  MegaLayer* s_ly = reinterpret_cast<MegaLayer*>(reinterpret_cast<uint8_t*>(s_slot_tab) + MG_SLOT_BYTES);
+  float* s_xown = s_stat + 784;
+  Ring rg;
+  rg.data = ring_data;
+  rg.data0 = smem_u32(ring_data);
+  rg.full0 = smem_u32(bars);
+  rg.empty0 = rg.full0 + 8 * MG_NSTAGE;
+  rg.unit = 0;
+  const uint32_t d_full = rg.full0 + 8 * (2 * MG_NSTAGE);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * MG_NSTAGE + 2);
+  const int tid = threadIdx.x;
+  if ((smem_u32(mg_smem) & 1023u) != 0) __trap();  // the swizzled operand tiles need 1024-byte alignment
+  if (tid == 0) {
+    for (int s = 0; s < MG_NSTAGE; ++s) {
+      mbar_init(rg.full(s), 1);
+      mbar_init(rg.empty(s), 1);
+    }
+    mbar_init(d_full, 1);
+    fence_mbar_init();
+  }
+  // rows of the B operand beyond the live ones are zero for the whole pass
+  for (int i = tid; i < MT_B_BYTES / 16; i += MG_THREADS) *reinterpret_cast<uint4*>(s_b + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < 32) {
+    tmem_alloc<64>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int L = A.n_layers;
+
+  if (tid >= MG_CONS) {
+    // ============================ producer: the static weight / KV stream of this CTA
+    if (tid == MG_CONS) {
+      for (int l = 0; l < L; ++l) {
+        const MegaLayer& ly = A.layers[l];
+        produce_gemv_tc(rg, ly.qkv);
+        produce_gemv_tc(rg, ly.o);
+        produce_gemv_tc(rg, ly.cq);
+        produce_cross(rg, A, ly);
+        produce_gemv_tc(rg, ly.co);
+        produce_gemv_tc(rg, ly.fc1);
+        produce_gemv_tc(rg, ly.fc2);
+      }
+      if (A.with_logits) produce_gemv_tc(rg, A.vocab);
+    }
+  } else {
+    // ============================== consumers
+    const int ctid = tid;
+    unsigned epoch = *A.epoch_base;
+    const unsigned epoch0 = epoch;
+    unsigned d_count = 0;
+    if (ctid == 0) *reinterpret_cast<int*>(s_stat + 1001) = 0;
+    auto prefetch_layer = [&](int l) {
+      if (ctid < static_cast<int>(sizeof(MegaLayer) / 16))
+        cp_async16(smem_u32(reinterpret_cast<uint8_t*>(s_ly) + (l & 1) * MG_LY_STRIDE) + ctid * 16,
+                   reinterpret_cast<const uint8_t*>(A.layers + l) + ctid * 16);
+    };
+    if (L > 0) prefetch_layer(0);
+    const int pos_dec = A.pf_len > 0 ? 0 : A.st->pos;
+    const int flipv = *A.flip;
+    if (A.pf_len == 0) {
+      const int task = blockIdx.x * MG_CONS_WARPS + (ctid >> 5);
+      if (task < A.R * A.H) {
+        const int* indir = (flipv ? A.indir1 : A.indir0) + static_cast<long long>(task / A.H) * A.t_max;
+        for (int t = ctid & 31; t < pos_dec; t += 32) s_slot_tab[(ctid >> 5) * 448 + t] = static_cast<unsigned short>(indir[t]);
+      }
+    }
+    cp_async_wait_all();
+    {
+      int lo, hi;
+      cta_cols(A.d, lo, hi);
+      for (int idx = ctid; idx < A.R * (hi - lo); idx += MG_CONS) {
+        const int r = idx / (hi - lo), c = idx - r * (hi - lo);
+        const float v = __half2float(A.tok_emb[static_cast<long long>(row_token(A, r)) * A.d + lo + c]) +
+                        A.pos_emb[static_cast<long long>(row_pos(A, r)) * A.d + lo + c];
+        s_xown[r * 16 + c] = v;
+        A.x[static_cast<long long>(r) * A.d + lo + c] = v;
+      }
+    }
+    grid_barrier(A, epoch, ctid, epoch0);
+    for (int l = 0; l < L; ++l) {
+      const MegaLayer& ly = *reinterpret_cast<const MegaLayer*>(reinterpret_cast<const uint8_t*>(s_ly) + (l & 1) * MG_LY_STRIDE);
+      if (l + 1 < L) prefetch_layer(l + 1);
+      consume_gemv_tc<NR>(rg, A, ly.qkv, &ly, ctid, s_b, s_red, s_xown, tmem_base, d_full, d_count);
+      grid_barrier(A, epoch, ctid, epoch0);
+      consume_self_attn(A, ly, ctid, reinterpret_cast<uint8_t*>(s_part), s_slot_tab, pos_dec, flipv);
+      grid_barrier(A, epoch, ctid, epoch0);
+      consume_gemv_tc<NR>(rg, A, ly.o, &ly, ctid, s_b, s_red, s_xown, tmem_base, d_full, d_count);
+      grid_barrier(A, epoch, ctid, epoch0);
+      consume_gemv_tc<NR>(rg, A, ly.cq, &ly, ctid, s_b, s_red, s_xown, tmem_base, d_full, d_count);
+      grid_barrier(A, epoch, ctid, epoch0);
+      consume_cross<NR, true>(rg, A, ctid, s_part, epoch + 1);
+      grid_barrier(A, epoch, ctid, epoch0);
+      consume_gemv_tc<NR>(rg, A, ly.co, &ly, ctid, s_b, s_red, s_xown, tmem_base, d_full, d_count);
+      grid_barrier(A, epoch, ctid, epoch0);
+      consume_gemv_tc<NR>(rg, A, ly.fc1, &ly, ctid, s_b, s_red, s_xown, tmem_base, d_full, d_count);
+      grid_barrier(A, epoch, ctid, epoch0);
+      consume_gemv_tc<NR>(rg, A, ly.fc2, &ly, ctid, s_b, s_red, s_xown, tmem_base, d_full, d_count);
+      cp_async_wait_all();
+      grid_barrier(A, epoch, ctid, epoch0);
+    }
+    if (A.with_logits) consume_gemv_tc<NR>(rg, A, A.vocab, nullptr, ctid, s_b, s_red, s_xown, tmem_base, d_full, d_count);
+    grid_barrier(A, epoch, ctid, epoch0);
+    if (blockIdx.x == 0 && ctid == 0) {
+      *A.epoch_base = epoch;
+      A.epoch_base[8] = epoch * gridDim.x;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc<64>(tmem_base);
 }
 
 __global__ void chunk_major_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int N, int K, int n_chunks) {
@@ -932,6 +1262,22 @@ void dec_pass_run(const MegaArgs& a, int num_sms, cudaStream_t stream) {
     attr_set = true;
   }
   void* args[] = {const_cast<MegaArgs*>(&a)};
+  if (a.tc) {
+    static bool tc_attr_done[64] = {};
+    bool& tc_set = tc_attr_done[dev & 63];
+    if (!tc_set) {
+      WISB_CUDA(cudaFuncSetAttribute(dec_pass_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM));
+      WISB_CUDA(cudaFuncSetAttribute(dec_pass_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM));
+      WISB_CUDA(cudaFuncSetAttribute(dec_pass_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM));
+      tc_set = true;
+    }
+    WISB_REQUIRE(a.d % 64 == 0 && 4 * a.d <= 5120, "tensor-core decoder pass: d_model <= 1280");
+    const void* fn_tc = a.R <= 2 ? reinterpret_cast<const void*>(dec_pass_tc_kernel<2>)
+                                 : a.R <= 5 ? reinterpret_cast<const void*>(dec_pass_tc_kernel<5>)
+                                            : reinterpret_cast<const void*>(dec_pass_tc_kernel<8>);
+    WISB_CUDA(cudaLaunchCooperativeKernel(fn_tc, dim3(num_sms), dim3(MG_THREADS), args, MT_SMEM, stream));
+    return;
+  }
   const void* fn = a.R <= 2 ? reinterpret_cast<const void*>(dec_pass_kernel<2>)
                             : a.R <= 5 ? reinterpret_cast<const void*>(dec_pass_kernel<5>)
                                        : reinterpret_cast<const void*>(dec_pass_kernel<8>);

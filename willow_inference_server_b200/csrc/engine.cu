@@ -145,6 +145,9 @@ struct wisb_handle {
   std::vector<BatchLayer> bd_layers;
   GemmPlan bd_vocab;
   DevBuf<MegaLayer> mega_layers;
+  DevBuf<CUtensorMap> mega_tmaps;  // tensor-core pass: one 2-D map per decoder weight matrix (6 per layer) + the vocabulary
+  std::vector<int> mega_rows_box, mega_kbu;
+  int mega_tc = 1;
   DevBuf<unsigned> mega_flags;
   // optional reuse of the encoder output + cross K/V between consecutive calls on identical host features
   // (detect_language -> generate -> translate on one window, main.py:633-644, 514-547): option "encoder_cache"
@@ -425,6 +428,39 @@ void finish_create(wisb_handle* h) {
       mega_chunk_major(h->dec_w[i].fc2w, h->fc2_chunked.p + per * i, d.d_model, 4 * d.d_model, h->stream);
   }
   h->cross_part.ensure(static_cast<size_t>(DEC_MAX_ROWS) * d.n_heads * 16 * MAX_BEAM * 68, true);
+  if (4 * d.d_model <= 5120) {
+    // tensor-core pass: 2-D tensor maps over the row-major decoder weights, box = 64 k x (the CTA's weight rows rounded up to
+    // whole 8-row swizzle atoms, at most 64); ring units of as many k-blocks as fit a 36 KB stage, evenly sized
+    const int n_maps = 6 * d.n_dec_layers + 1;
+    std::vector<CUtensorMap> maps(n_maps);
+    h->mega_rows_box.assign(n_maps, 0);
+    h->mega_kbu.assign(n_maps, 0);
+    auto make = [&](int idx, const __half* w, int N, int K, int rows_total) {
+      const int per = (N + h->num_sms - 1) / h->num_sms;
+      const int rows_box = round_up(per < 64 ? per : 64, 8);
+      const int kblocks = K / 64;
+      const int max_kbu = 36864 / (rows_box * 128);
+      const int n_units = (kblocks + max_kbu - 1) / max_kbu;
+      h->mega_rows_box[idx] = rows_box;
+      h->mega_kbu[idx] = (kblocks + n_units - 1) / n_units;
+      make_tmap_f16_2d(&maps[idx], w, K, rows_total, K, 64, rows_box);
+    };
+    const int dd = d.d_model;
+    for (int i = 0; i < d.n_dec_layers; ++i) {
+      const DecLayerW& w = h->dec_w[i];
+      make(6 * i + 0, w.qkvw, 3 * dd, dd, 3 * dd);
+      make(6 * i + 1, w.ow, dd, dd, dd);
+      make(6 * i + 2, w.cqw, dd, dd, dd);
+      make(6 * i + 3, w.cow, dd, dd, dd);
+      make(6 * i + 4, w.fc1w, 4 * dd, dd, 4 * dd);
+      make(6 * i + 5, w.fc2w, dd, 4 * dd, dd);
+    }
+    make(6 * d.n_dec_layers, h->H("dec.tok_emb"), d.n_vocab, dd, d.n_vocab_pad);
+    h->mega_tmaps.ensure(n_maps);
+    WISB_CUDA(cudaMemcpy(h->mega_tmaps.p, maps.data(), sizeof(CUtensorMap) * n_maps, cudaMemcpyHostToDevice));
+  } else {
+    h->mega_tc = 0;
+  }
   WISB_CUDA(cudaStreamSynchronize(h->stream));
 }
 
@@ -678,8 +714,16 @@ void upload_mega_layers(wisb_handle* h, const DecodeCfg& c) {
     set(m.cq, w.cqw, fb + 7 * d, w.ln2g, fb + 6 * d, h->dx.p, h->dq.p, d, d, d, GV_STORE);
     set(m.co, w.cow, w.cob, nullptr, nullptr, h->dctx.p, h->dx.p, d, d, d, GV_RESID);
     set(m.fc1, w.fc1w, fb + 12 * d, w.ln3g, fb + 8 * d, h->dx.p, h->dh.p, 4 * d, 4 * d, d, GV_GELU);
-    const __half* fc2w = h->fc2_chunked.p ? h->fc2_chunked.p + static_cast<size_t>(4) * d * d * i : w.fc2w;
+    const __half* fc2w = (h->fc2_chunked.p && !h->mega_tc) ? h->fc2_chunked.p + static_cast<size_t>(4) * d * d * i : w.fc2w;
     set(m.fc2, fc2w, w.fc2b, nullptr, nullptr, h->dh.p, h->dx.p, d, d, 4 * d, GV_RESID);
+    if (h->mega_tc) {
+      MegaGemv* gs[6] = {&m.qkv, &m.o, &m.cq, &m.co, &m.fc1, &m.fc2};
+      for (int j = 0; j < 6; ++j) {
+        gs[j]->tmap = h->mega_tmaps.p + 6 * i + j;
+        gs[j]->rows_box = h->mega_rows_box[6 * i + j];
+        gs[j]->kbu = h->mega_kbu[6 * i + j];
+      }
+    }
     m.ck = h->ckv.p + (static_cast<size_t>(i * 2 + 0) * c.B_total + c.u0) * head_block;
     m.cv = h->ckv.p + (static_cast<size_t>(i * 2 + 1) * c.B_total + c.u0) * head_block;
     m.kcache = h->kcache.p + i * layer_cache;
@@ -708,6 +752,13 @@ int enqueue_decoder_forward_mega(wisb_handle* h, const DecodeCfg& c, bool with_l
   a.vocab.N = dm.n_vocab;
   a.vocab.K = dm.d_model;
   a.vocab.epi = GV_STORE;
+  if (h->mega_tc) {
+    const int vi = 6 * dm.n_dec_layers;
+    a.vocab.tmap = h->mega_tmaps.p + vi;
+    a.vocab.rows_box = h->mega_rows_box[vi];
+    a.vocab.kbu = h->mega_kbu[vi];
+    a.tc = 1;
+  }
   a.with_logits = with_logits ? 1 : 0;
   a.R = c.n_utt * c.beam;
   a.d = dm.d_model;
@@ -1344,6 +1395,10 @@ int wisb_set_option(wisb_handle* h, const char* key, int value) {
     else if (k == "batch_pdl") h->batch_pdl = value ? 1 : 0;
     else if (k == "mega_barrier") h->mega_barrier = value ? 1 : 0;
     else if (k == "debug_chunk") h->debug_chunk = value;
+    else if (k == "mega_tc") {  // 1: GEMV phases of the persistent pass on tcgen05, 0: the SIMT pass
+      WISB_REQUIRE(!value || h->mega_tmaps.p != nullptr, "mega_tc needs d_model <= 1280");
+      h->mega_tc = value ? 1 : 0;
+    }
     else if (k == "cross_tc") {  // 1: tcgen05 cross-attention in the batched pass, 0: the SIMT cluster kernel (cross-check)
       h->cross_tc = value ? 1 : 0;
       drop_graphs(h);
@@ -1581,6 +1636,27 @@ int wisb_debug_gemm(wisb_handle* h, const uint16_t* a, const uint16_t* w, float*
       gemm_run(p, s);
     }
     WISB_CUDA(cudaMemcpyAsync(c, dc.p, sizeof(float) * M * N, cudaMemcpyDeviceToHost, s));
+    WISB_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int wisb_debug_gemv_tc(wisb_handle* h, const float* x, const uint16_t* w, const float* bias, float* out, int R, int N, int K,
+                       int iters, float* avg_us) {
+  return guarded(h, [&] {
+    WISB_REQUIRE(x && w && out, "NULL pointer");
+    cudaStream_t s = h->stream;
+    DevBuf<float> dx, db, dout;
+    DevBuf<__half> dw;
+    dx.ensure(static_cast<size_t>(R) * K);
+    dw.ensure(static_cast<size_t>(N) * K);
+    db.ensure(static_cast<size_t>(N));
+    dout.ensure(static_cast<size_t>(R) * N, true);
+    WISB_CUDA(cudaMemcpyAsync(dx.p, x, sizeof(float) * R * K, cudaMemcpyHostToDevice, s));
+    WISB_CUDA(cudaMemcpyAsync(dw.p, w, sizeof(__half) * static_cast<size_t>(N) * K, cudaMemcpyHostToDevice, s));
+    if (bias) WISB_CUDA(cudaMemcpyAsync(db.p, bias, sizeof(float) * N, cudaMemcpyHostToDevice, s));
+    const float us = gemv_tc_debug_run(dx.p, dw.p, bias ? db.p : nullptr, dout.p, R, N, K, h->num_sms, iters, s);
+    if (avg_us) *avg_us = us;
+    WISB_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(float) * R * N, cudaMemcpyDeviceToHost, s));
     WISB_CUDA(cudaStreamSynchronize(s));
   });
 }
