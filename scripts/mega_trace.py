@@ -14,13 +14,15 @@ pcm = torch.from_numpy(bench.synth_utterance(bench.AUDIO_SAMPLES, 1234)).cuda()
 off, ns = np.zeros(1, np.int64), np.array([bench.AUDIO_SAMPLES], np.int32)
 prompts = np.array([bench.PROMPT], np.int32)
 h.set_option("mega_trace", 1)
+if "--mma" in sys.argv:
+    h.set_option("mega_mma", 1)
 for i in range(3):
     h.logmel(pcm.data_ptr(), off, ns, to_host=False, keep=True, pcm_on_device=True, pcm_dtype=_lib.PCM_F32, B=1)
     ids, _ = h.generate(None, prompts, bench.BEAM, 1.0, 1.0, bench.MAX_LENGTH, [dims.eot], B=1)
 print(h.timing())
 tt = h.debug_read_trace(2048).astype(np.int64)
-ev = tt[1024:1024+2*120].reshape(-1,2)
-print('events (id, t ns, dt):', [(int(a), int(b - ev[0,1]), int(b - ev[max(i-1,0),1])) for i, (a, b) in enumerate(ev[:70])])
+ev = tt[1024:1024+2*240].reshape(-1,2)
+print('events (id, t ns, dt):', [(int(a), int(b - ev[0,1]), int(b - ev[max(i-1,0),1])) for i, (a, b) in enumerate(ev[:110])])
 t = tt[:2*262]
 # t[2k] = time barrier k was released (k=0: kernel start), t[2k+1] = time CTA 0 arrived at barrier k+1... (index k -> barrier k+1)
 rel = t[0::2]; arr = t[1::2]

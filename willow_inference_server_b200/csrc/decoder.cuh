@@ -143,7 +143,7 @@ int batch_pass_run(const BatchArgs& a, const BatchLayer* layers, int n_layers, c
 
 // ------------------------------------------------------------------ persistent decoder pass (decoder_mega.cu)
 struct MegaGemv {
-  const __half* w = nullptr;     // [N, K] fp16; K > 1536: chunk-major [chunk][N][K/chunks] (mega_chunk_major)
+  const __half* w = nullptr;     // [N, K] fp16; K > 1536: chunk-major [chunk][N][K/chunks] (mega_chunk_major); warp-MMA pass: mega_mma_image
   const float* bias = nullptr;
   const float* ln_g = nullptr;   // LayerNorm gamma (x is multiplied by it while staged), K <= 1536
   const float* ln_s2 = nullptr;  // non-null = LayerNorm folded: s2[n] = sum_k g_k W[n,k]; `bias` then holds bias + sum_k b_k W[n,k]
@@ -151,10 +151,11 @@ struct MegaGemv {
   float* out = nullptr;
   long long ldo = 0;
   int N = 0, K = 0, epi = GV_STORE;
-  // tensor-core pass (dec_pass_tc_kernel): 2-D tensor map over the row-major W [N, K] (box = 64 k x rows_box weight rows,
-  // 128-byte swizzle; device memory, 64-byte aligned), weight rows per box, k-blocks per ring unit
-  const CUtensorMap* tmap = nullptr;
-  int rows_box = 0, kbu = 0;
+  int shape = 0;                 // warp-MMA pass: 0 qkv, 1 d x d (o / cross-q / cross-o), 2 fc1, 3 fc2, 4 vocabulary (geometry table)
+  // fp16 activation exchange images [K/64][R][64] (decoder_mega.cu act16_off): input read with one bulk copy / GELU output
+  const __half* x16 = nullptr;
+  __half* out16 = nullptr;
+  const float* next_g = nullptr;  // GV_RESID: gain of the LayerNorm that reads the new residual rows next
 };
 struct MegaLayer {
   MegaGemv qkv, o, cq, co, fc1, fc2;
@@ -178,6 +179,9 @@ struct MegaArgs {
   float* x = nullptr;      // [R, d] residual stream
   float* q = nullptr;      // [R, d]
   float* ctx = nullptr;    // [R, d]
+  __half* ctx16 = nullptr; // warp-MMA pass: attention output as an fp16 exchange image instead of `ctx`
+  __half* xn16 = nullptr;  // warp-MMA pass: residual rows times the next LayerNorm's gain, fp16 exchange image
+  float* xstat = nullptr;  // warp-MMA pass: [CTA][R][2] per-CTA shares of the rows' (sum, sum of squares)
   const int* indir0 = nullptr;
   const int* indir1 = nullptr;
   const int* flip = nullptr;
@@ -187,12 +191,14 @@ struct MegaArgs {
   unsigned* flags = nullptr;     // grid-barrier epoch flags, one 128-byte line per CTA
   unsigned* epoch_base = nullptr;
   int barrier_mode = 0;          // 0: per-CTA epoch flags, 1: shared counter (red.release + spin)
-  int tc = 0;                    // 1: GEMV phases on tcgen05 (dec_pass_tc_kernel)
+  int tc = 0;                    // 1: GEMV phases on the warp-level tensor path (dec_pass_mma_kernel)
   unsigned long long* trace = nullptr;  // optional: [2*k] = time phase k starts, [2*k+1] = time CTA 0 reached barrier k
 };
 size_t mega_flags_words();
 int mega_k_chunks(int K);
 void mega_chunk_major(const __half* src, __half* dst, int N, int K, cudaStream_t stream);
+// W [N, K] -> the image the warp-MMA pass streams with one bulk copy per ring unit ((N rounded up to 8) x K halves)
+void mega_mma_image(const __half* src, __half* dst, int N, int K, int grid, cudaStream_t stream);
 // s2[n] = sum_k g[k] W[n,k];  biasf[n] = bias[n] + sum_k b[k] W[n,k]   (bias may be null)
 void mega_ln_fold(const __half* w, const float* g, const float* b, const float* bias, float* s2, float* biasf, int N, int K,
                   cudaStream_t stream);

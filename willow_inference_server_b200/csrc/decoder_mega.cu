@@ -37,7 +37,7 @@ constexpr int MG_NSTAGE = 2;
 constexpr int MG_CA_KEYS_MAX = MG_STAGE_BYTES / 128;    // 288 keys per K (or V) chunk
 constexpr int MG_SCRATCH = 29696;                       // self-attention V rows + probabilities / cross-attention merge
 constexpr int MG_SLOT_BYTES = MG_CONS_WARPS * 448 * 2;  // per-warp cache-slot table of the warp's self-attention task
-constexpr int MG_LY_STRIDE = 640;
+constexpr int MG_LY_STRIDE = 704;
 constexpr int MG_LY_BYTES = 2 * MG_LY_STRIDE;           // double-buffered copy of the layer descriptor
 constexpr int MG_RED_FLOATS = (2 * 2 + 1) * MG_CONS_WARPS * 32;  // 2 buffers x 2 sets + LN partials
 constexpr int MG_SMEM = MG_NSTAGE * MG_STAGE_BYTES + 1024 + MG_RED_FLOATS * 4 + 4224 + MG_SCRATCH + MG_SLOT_BYTES + MG_LY_BYTES;
@@ -95,6 +95,22 @@ __device__ __forceinline__ int row_pos(const MegaArgs& A, int r) { return A.pf_l
 __device__ __forceinline__ int row_slot(const MegaArgs& A, int r) { return A.pf_len > 0 ? (r / A.pf_len) * A.pf_slot_stride : r; }
 __device__ __forceinline__ int row_token(const MegaArgs& A, int r) {
   return A.pf_len > 0 ? A.tokens[(r / A.pf_len) * A.pf_tok_stride + (r % A.pf_len)] : A.tokens[r];
+}
+
+
+// fp16 activation exchange of the warp-MMA pass: element (row r, feature k) of a [K/64 k-blocks][R rows][128 B] buffer whose
+// 16-byte chunks are XOR-swizzled by the row -- exactly the B-operand image a consumer CTA wants in shared memory, so its
+// reload is ONE bulk copy (scripts/ubench_reload: 0.7 us against 1.4 us for the ld.global reload of the same 25.6 KB)
+__device__ __forceinline__ long long act16_off(int R, int r, int k) {
+  return static_cast<long long>(k >> 6) * (R * 64) + r * 64 + ((((k >> 3) & 7) ^ r) << 3) + (k & 7);
+}
+// attention output of row r, features [col, col + 2): fp32 [R, d] (SIMT pass) or the fp16 exchange image (warp-MMA pass)
+__device__ __forceinline__ void store_ctx2(const MegaArgs& A, int r, int col, float v0, float v1) {
+  if (A.ctx16 != nullptr) {
+    *reinterpret_cast<__half2*>(A.ctx16 + act16_off(A.R, r, col)) = __floats2half2_rn(v0, v1);
+  } else {
+    *reinterpret_cast<float2*>(A.ctx + static_cast<long long>(r) * A.d + col) = make_float2(v0, v1);
+  }
 }
 
 struct Ring {
@@ -165,6 +181,7 @@ __device__ __forceinline__ CrossGeom cross_geom(int n_utt, int H) {
   return c;
 }
 
+template <int NS = MG_NSTAGE>
 __device__ __noinline__ void produce_cross(Ring& rg, const MegaArgs& A, const MegaLayer& ly) {
   const CrossGeom cg = cross_geom(A.n_utt, A.H);
   const uint64_t pol = l2_policy_evict_first();
@@ -174,8 +191,8 @@ __device__ __noinline__ void produce_cross(Ring& rg, const MegaArgs& A, const Me
     const int nk = min(cg.KS, T_ENC_PAD - t0);  // buffer has 1536 rows; keys >= 1500 are skipped by the consumer
     const long long off = (static_cast<long long>(uh) * T_ENC_PAD + t0) * HEAD_DIM;
     for (int kv = 0; kv < 2; ++kv) {
-      const int st = rg.unit % MG_NSTAGE;
-      mbar_wait(rg.empty(st), ((rg.unit / MG_NSTAGE) & 1u) ^ 1u);
+      const int st = rg.unit % NS;
+      mbar_wait(rg.empty(st), ((rg.unit / NS) & 1u) ^ 1u);
       mbar_arrive_expect_tx(rg.full(st), static_cast<uint32_t>(nk * HEAD_DIM * 2));
       bulk_load_1d_hint(rg.data0 + st * MG_STAGE_BYTES, (kv == 0 ? ly.ck : ly.cv) + off,
                         static_cast<uint32_t>(nk * HEAD_DIM * 2), rg.full(st), pol);
@@ -462,7 +479,7 @@ __device__ __noinline__ void consume_gemv(Ring& rg, const MegaArgs& A, const Meg
 // P.V product then runs from shared memory with lanes over the head dimension.  The step position, the ping-pong flag and
 // the warp's cache-slot table are pass constants, read once at kernel start (`pos_dec`, `flipv`, `s_slot_tab`).
 __device__ __noinline__ void consume_self_attn(const MegaArgs& A, const MegaLayer& ly, int ctid, uint8_t* s_scr,
-                                               const unsigned short* s_slot_tab, int pos_dec, int flipv) {
+                                               const unsigned short* s_slot_tab, int pos_dec, int flipv, int* s_tr) {
   const int lane = ctid & 31, warp = ctid >> 5;
   const int d = A.d, H = A.H;
   const int n_tasks = A.R * H;
@@ -472,7 +489,6 @@ __device__ __noinline__ void consume_self_attn(const MegaArgs& A, const MegaLaye
   const unsigned short* my_slots = s_slot_tab + warp * 448;
   const __half* kcache = ly.kcache;
   const __half* vcache = ly.vcache;
-  int* s_tr = reinterpret_cast<int*>(s_scr) - 55;  // = s_stat + 1001 (trace cursor)
   trace_ev(A, ctid, s_tr, 20);
   for (int base = blockIdx.x * MG_CONS_WARPS; base < n_tasks; base += gridDim.x * MG_CONS_WARPS) {
     const int task = base + warp;
@@ -539,7 +555,7 @@ __device__ __noinline__ void consume_self_attn(const MegaArgs& A, const MegaLaye
       }
       trace_ev(A, ctid, s_tr, 23);
       const float inv = 1.0f / l;
-      *reinterpret_cast<float2*>(A.ctx + static_cast<long long>(r) * d + h * HEAD_DIM + 2 * lane) = make_float2(o0 * inv, o1 * inv);
+      store_ctx2(A, r, h * HEAD_DIM + 2 * lane, o0 * inv, o1 * inv);
       trace_ev(A, ctid, s_tr, 24);
     }
   }
@@ -551,19 +567,17 @@ __device__ __noinline__ void consume_self_attn(const MegaArgs& A, const MegaLaye
 // last split of a head to arrive (atomic counter) merges the S partials into ctx.
 // kOneArrive: the ring's empty barriers count ONE arrival per stage (tensor-core pass: tcgen05.commit releases the weight
 // stages) instead of one per consumer warp
-template <int NB, bool kOneArrive = false>
-__device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid, float* s_part, unsigned tag) {
+template <int NB, bool kOneArrive = false, int NS = MG_NSTAGE>
+__device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid, float* s_part, unsigned tag, int* s_tr) {
   const int grp = ctid >> 3, gl = ctid & 7;
   constexpr int NGRP = MG_CONS / 8;  // 28
   const int d = A.d, beam = A.beam, H = A.H;
   const float* qbase = A.q;
-  float* ctx = A.ctx;
   float* cross_part = A.cross_part;
   const uint32_t ring_data0 = rg.data0, ring_full0 = rg.full0, ring_empty0 = rg.empty0;
   unsigned unit = rg.unit;
   const unsigned gmask = 0xFFu << (ctid & 24);
   const CrossGeom cg = cross_geom(A.n_utt, H);
-  int* s_tr = reinterpret_cast<int*>(s_part) - 55;  // = s_stat + 1001 (trace cursor)
   trace_ev(A, ctid, s_tr, 10);
   for (int task = blockIdx.x; task < cg.n_tasks; task += gridDim.x) {
     const int split = task % cg.S, uh = task / cg.S;
@@ -592,9 +606,9 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
       for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
     }
     trace_ev(A, ctid, s_tr, 11);
-    const int stK = unit % MG_NSTAGE, stV = (unit + 1) % MG_NSTAGE;
-    mbar_wait(ring_full0 + 8u * stK, (unit / MG_NSTAGE) & 1u);
-    mbar_wait(ring_full0 + 8u * stV, ((unit + 1) / MG_NSTAGE) & 1u);
+    const int stK = unit % NS, stV = (unit + 1) % NS;
+    mbar_wait(ring_full0 + 8u * stK, (unit / NS) & 1u);
+    mbar_wait(ring_full0 + 8u * stV, ((unit + 1) / NS) & 1u);
     const uint32_t sK = ring_data0 + stK * MG_STAGE_BYTES, sV = ring_data0 + stV * MG_STAGE_BYTES;
     trace_ev(A, ctid, s_tr, 12);
 #pragma unroll 1
@@ -750,7 +764,7 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
           ll = fmaf(w, ml[s2].y, ll);
         }
         const float inv = 1.f / ll;
-        *reinterpret_cast<float2*>(ctx + static_cast<long long>(u * beam + k) * d + h * HEAD_DIM + e) = make_float2(ax * inv, ay * inv);
+        store_ctx2(A, u * beam + k, h * HEAD_DIM + e, ax * inv, ay * inv);
       }
     }
     trace_ev(A, ctid, s_tr, 17);
@@ -846,13 +860,13 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs 
     if (l + 1 < L) prefetch_layer(l + 1);  // the other buffer was last read in layer l - 1
     consume_gemv<NR>(rg, A, ly.qkv, &ly, ctid, s_red, s_stat);
     grid_barrier(A, epoch, ctid, epoch0);
-    consume_self_attn(A, ly, ctid, reinterpret_cast<uint8_t*>(s_part), s_slot_tab, pos_dec, flipv);
+    consume_self_attn(A, ly, ctid, reinterpret_cast<uint8_t*>(s_part), s_slot_tab, pos_dec, flipv, reinterpret_cast<int*>(s_stat + 1001));
     grid_barrier(A, epoch, ctid, epoch0);
     consume_gemv<NR>(rg, A, ly.o, &ly, ctid, s_red, s_stat);
     grid_barrier(A, epoch, ctid, epoch0);
     consume_gemv<NR>(rg, A, ly.cq, &ly, ctid, s_red, s_stat);
     grid_barrier(A, epoch, ctid, epoch0);
-    consume_cross<NR>(rg, A, ctid, s_part, epoch + 1);  // beam <= rows <= NR; tag = a value unique to this phase
+    consume_cross<NR>(rg, A, ctid, s_part, epoch + 1, reinterpret_cast<int*>(s_stat + 1001));  // beam <= rows <= NR; tag = a value unique to this phase
     grid_barrier(A, epoch, ctid, epoch0);
     consume_gemv<NR>(rg, A, ly.co, &ly, ctid, s_red, s_stat);
     grid_barrier(A, epoch, ctid, epoch0);
@@ -873,242 +887,352 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs 
 
 
 // =====================================================================================================================
-// Tensor-core variant of the pass: the six GEMV phases of a layer and the vocabulary projection run on tcgen05
-// (swap-AB skinny GEMV, see gemv_tc.cu): the CTA's weight rows are the MMA's M (64, of which the CTA owns <= 40; the
-// vocabulary slice is walked in groups of 64), the <= 8 activation rows its N.  What disappears against the SIMT pass:
-// the fp32 FMA loop over the weight stage, the transposing shuffle reductions and the shared-memory hop of every phase.
-// What stays: the producer thread and its static weight schedule (now 2-D TMA boxes straight from the row-major W), the
-// grid barrier between phases, the attention phases, LayerNorm folded into the epilogue, residual columns owned by the CTA.
+// Warp-MMA variant of the pass: the six GEMV phases of a layer and the vocabulary projection run on the warp-level tensor
+// path (mma.sync.m16n8k16, fp16 x fp16 -> fp32): the CTA's weight rows are the MMA's M (16-row tiles), the <= 8 activation
+// rows its N, K is split over the 7 consumer warps and their partial tiles are summed through shared memory.
+// Why not tcgen05 here (it is what the encoder, the batched pass and the cross-attention of the batched pass use): at
+// N = 8 a tcgen05.mma of 64 x 8 x 16 is issue-latency bound at ~50 cycles (scripts/diag_gemv_tc.py: 8.2 us for ANY of the
+// layer shapes, 16.8 us at K = 5120), so a K = 1280 phase costs 2 us and fc2 8 us -- slower than the fp32 FMA loop it was
+// meant to replace (the tcgen05 pass measured 43.1 ms per 16 passes against 29.6 ms).  The warp MMA has no such floor:
+// 18 (k-block, m-tile) items of 4 HMMAs each per warp cover the QKV phase.  What disappears against the SIMT pass: the
+// fp32 FMA loop over the weight stage (1.05 us per 12 columns) and the transposing shuffle reductions.  What stays: the
+// producer thread and its static weight schedule (2-D TMA boxes, 128-byte swizzle, straight from the row-major W -- the
+// swizzle is what makes ldmatrix conflict-free), the grid barrier between phases, the attention phases, LayerNorm folded
+// into the epilogue, residual columns owned by the CTA.  Columns are dealt to the CTAs in whole octets (8-row swizzle
+// atoms), so no CTA streams a neighbour's weight rows.
 // Activations are rounded to fp16 when they become the B operand (the encoder and the batched pass do the same).
 // =====================================================================================================================
-constexpr int MT_B_BYTES = 80 * 1024;   // B operand: K / 64 k-blocks x [8 rows x 128 B]  (K <= 5120)
-constexpr int MT_OFF_B = MG_NSTAGE * MG_STAGE_BYTES;  // (the MMA's 64-row read may run up to 8 KB past a stage: into B, harmless)
-constexpr int MT_OFF_BARS = MT_OFF_B + MT_B_BYTES;
-constexpr int MT_SMEM = MT_OFF_BARS + 1024 + MG_RED_FLOATS * 4 + 4224 + MG_SCRATCH + MG_SLOT_BYTES + MG_LY_BYTES + 1024;
-static_assert(MT_SMEM <= 232448, "tensor-core decoder pass: shared memory");
+// shared-memory plan of the warp-MMA kernel: ring | B operand (aliased by the attention scratch) | partial tiles | barriers,
+// statistics, trace cursor, owned residual columns | cache-slot tables | layer descriptors | phase geometry
+template <int NR>
+struct MmaSmem {
+  static constexpr int NS = NR <= 5 ? 4 : 3;                 // ring stages: a whole next phase's weights fit ahead of the consumers
+  static constexpr int B_BYTES = (5120 / 64) * NR * 128;     // B operand image of the largest K (fc2): [K/64][R][128 B]
+  static constexpr int B_ALLOC = B_BYTES > MG_SCRATCH ? B_BYTES : MG_SCRATCH;
+  static constexpr int OFF_B = NS * MG_STAGE_BYTES;          // (an m-tile's 16-row read may run 1 KB past its box: harmless)
+  static constexpr int OFF_PART = OFF_B + B_ALLOC;
+  static constexpr int PART_BYTES = MG_CONS_WARPS * 8 * 68 * 4;
+  static constexpr int OFF_BARS = OFF_PART + PART_BYTES;
+  static constexpr int OFF_STAT = OFF_BARS + 256;            // 1056 floats, same map as the SIMT kernel's s_stat
+  static constexpr int OFF_SLOT = OFF_STAT + 4224;
+  static constexpr int OFF_LY = OFF_SLOT + MG_SLOT_BYTES;
+  static constexpr int OFF_GEOM = OFF_LY + MG_LY_BYTES;
+  static constexpr int TOTAL = OFF_GEOM + 5 * 64;
+  static constexpr int STAT_OFF = 24576;                     // row-statistics shares land behind the image of a K <= 1280 phase
+  static_assert(TOTAL <= 232448, "warp-MMA decoder pass: shared memory");
+  static_assert(20 * NR * 128 <= STAT_OFF && STAT_OFF + 160 * NR * 8 <= B_ALLOC, "statistics landing zone");
+};
+constexpr int MM_GROUP_ROWS = 64;       // weight rows per accumulation group (4 m-tiles)
+constexpr int MM_PART_LD = 68;          // partial tiles [warp][8 rows][68]: conflict-free fragment stores
 
-__device__ __noinline__ void produce_gemv_tc(Ring& rg, const MegaGemv& g) {
-  int lo, hi;
-  cta_cols(g.N, lo, hi);
-  const int n_groups = (hi - lo + 63) / 64;
+// columns of a GEMV phase owned by this CTA, in whole octets: the first `oct % grid` CTAs own one octet more; ring units of a
+// group of `rows` weight rows: as many 64-wide k-blocks as fit a stage, evenly sized.  Computed once per kernel for the five
+// GEMV shapes (qkv, d x d, fc1, fc2, vocabulary): at one warp per scheduler every instruction on a phase's critical path
+// costs ~2.5 ns, the integer divisions of this would be 0.4 us per phase.
+struct MmaGeom {
+  int lo, hi, rows_pad, n_full, tail;
+  int units_full, kbu_full, units_tail, kbu_tail, pad[7];
+};
+static_assert(sizeof(MmaGeom) == 64, "geometry table stride");
+__device__ __forceinline__ void mma_units(int rows, int kblocks, int& units, int& kbu) {
+  const int max_kbu = MG_STAGE_BYTES / (rows * 128);
+  units = (kblocks + max_kbu - 1) / max_kbu;
+  kbu = (kblocks + units - 1) / units;
+}
+__device__ __forceinline__ MmaGeom mma_geom(int N, int K) {
+  MmaGeom m;
+  const int oct = (N + 7) >> 3, G = static_cast<int>(gridDim.x), b = static_cast<int>(blockIdx.x);
+  const int base = oct / G, rem = oct - base * G;
+  const int no = base + (b < rem ? 1 : 0);
+  m.lo = (b * base + min(b, rem)) * 8;
+  m.rows_pad = no * 8;
+  m.hi = min(N, m.lo + m.rows_pad);
+  m.n_full = m.rows_pad / MM_GROUP_ROWS;
+  m.tail = m.rows_pad - m.n_full * MM_GROUP_ROWS;
+  m.units_full = m.kbu_full = m.units_tail = m.kbu_tail = 0;
+  if (m.n_full > 0) mma_units(MM_GROUP_ROWS, K / 64, m.units_full, m.kbu_full);
+  if (m.tail > 0) mma_units(m.tail, K / 64, m.units_tail, m.kbu_tail);
+  return m;
+}
+
+template <int NS>
+__device__ __noinline__ void produce_gemv_mma(Ring& rg, const MegaGemv& g, const MmaGeom* s_geom) {
+  const MmaGeom mg = s_geom[g.shape];
+  const int n_groups = mg.n_full + (mg.tail ? 1 : 0);
   const int kblocks = g.K / 64;
-  const int units = (kblocks + g.kbu - 1) / g.kbu;
   const uint64_t pol = l2_policy_evict_first();
   for (int gi = 0; gi < n_groups; ++gi) {
-    const int row0 = lo + gi * 64;
+    const bool full = gi < mg.n_full;
+    const int rows = full ? MM_GROUP_ROWS : mg.tail;
+    const int units = full ? mg.units_full : mg.units_tail, kbu = full ? mg.kbu_full : mg.kbu_tail;
+    // g.w is the warp-MMA image of W (mma_image_kernel): the group's k-blocks are contiguous [k-block][rows][128 B swizzled]
+    const __half* base = g.w + static_cast<long long>(mg.lo + gi * MM_GROUP_ROWS) * g.K;
     for (int u = 0; u < units; ++u) {
-      const int kb0 = u * g.kbu, nkb = min(g.kbu, kblocks - kb0);
-      const int st = rg.unit % MG_NSTAGE;
-      mbar_wait(rg.empty(st), ((rg.unit / MG_NSTAGE) & 1u) ^ 1u);
-      mbar_arrive_expect_tx(rg.full(st), static_cast<uint32_t>(nkb * g.rows_box * 128));
-      for (int i = 0; i < nkb; ++i)
-        tma_load_2d_hint(rg.data0 + st * MG_STAGE_BYTES + i * g.rows_box * 128, g.tmap, rg.full(st), (kb0 + i) * 64, row0, pol);
+      const int kb0 = u * kbu, nkb = min(kbu, kblocks - kb0);
+      const int st = rg.unit % NS;
+      mbar_wait(rg.empty(st), ((rg.unit / NS) & 1u) ^ 1u);
+      mbar_arrive_expect_tx(rg.full(st), static_cast<uint32_t>(nkb * rows * 128));
+      bulk_load_1d_hint(rg.data0 + st * MG_STAGE_BYTES, base + static_cast<long long>(kb0) * rows * 64,
+                        static_cast<uint32_t>(nkb * rows * 128), rg.full(st), pol);
       ++rg.unit;
     }
   }
 }
 
-template <int NR>
-__device__ __noinline__ void consume_gemv_tc(Ring& rg, const MegaArgs& A, const MegaGemv& g_mem, const MegaLayer* ly, int ctid,
-                                            uint8_t* s_b, float* s_lnred, float* s_xown, uint32_t tmem_base, uint32_t d_full,
-                                            unsigned& d_count) {
-  const MegaGemv g = g_mem;
-  const int lane = ctid & 31, warp = ctid >> 5;
-  const int R = A.R;
-  int lo, hi;
-  cta_cols(g.N, lo, hi);
-  const int n_groups = (hi - lo + 63) / 64;
-  const int kblocks = g.K / 64;
-  const int units = (kblocks + g.kbu - 1) / g.kbu;
-  const bool ln = g.ln_s2 != nullptr;
-  // ---- B operand: x (times the LayerNorm gain) -> fp16, [k-block][8 rows][128 B], 16-byte chunks XOR-swizzled by the row;
-  //      the LayerNorm statistics (single pass, fp32) ride along
-  float sx[NR], sxx[NR];
+// New residual-stream value of (row r, column n) leaves its owner CTA three ways: fp32 into `x` (debug / other passes),
+// fp16 times the NEXT LayerNorm's gain into the exchange image the next LN-GEMV phase bulk-loads as its B operand, and as
+// this CTA's share of the row's LayerNorm statistics (sum, sum of squares over its <= 16 columns) -- the consumers add the
+// per-CTA shares in a fixed order, so the statistics are deterministic and nobody re-reads the fp32 row.
+// Thread mapping: 16 consecutive lanes = one row; every lane of the warp must call (shuffles).
+__device__ __forceinline__ void publish_resid(const MegaArgs& A, int r, int n, bool valid, float nv, float gain, int lane) {
+  float s1 = valid ? nv : 0.f, s2 = valid ? nv * nv : 0.f;
 #pragma unroll
-  for (int r = 0; r < NR; ++r) sx[r] = sxx[r] = 0.f;
-  for (int v = ctid; v < g.K / 8; v += MG_CONS) {
-    const int kb = v >> 3, c = v & 7;
-    float gg[8];
-    if (ln) {
-      const float4 g0v = __ldg(reinterpret_cast<const float4*>(g.ln_g + v * 8)), g1v = __ldg(reinterpret_cast<const float4*>(g.ln_g + v * 8 + 4));
-      gg[0] = g0v.x; gg[1] = g0v.y; gg[2] = g0v.z; gg[3] = g0v.w; gg[4] = g1v.x; gg[5] = g1v.y; gg[6] = g1v.z; gg[7] = g1v.w;
-    }
-    float4 x0[NR], x1[NR];
-#pragma unroll
-    for (int r = 0; r < NR; ++r)
-      if (r < R) {
-        x0[r] = ldcg_f4(g.x + static_cast<long long>(r) * g.K + v * 8);
-        x1[r] = ldcg_f4(g.x + static_cast<long long>(r) * g.K + v * 8 + 4);
-      }
-#pragma unroll
-    for (int r = 0; r < NR; ++r)
-      if (r < R) {
-        float xv[8] = {x0[r].x, x0[r].y, x0[r].z, x0[r].w, x1[r].x, x1[r].y, x1[r].z, x1[r].w};
-        if (ln) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            sx[r] += xv[i];
-            sxx[r] = fmaf(xv[i], xv[i], sxx[r]);
-            xv[i] *= gg[i];
-          }
-        }
-        __half2 h0 = __floats2half2_rn(xv[0], xv[1]), h1 = __floats2half2_rn(xv[2], xv[3]);
-        __half2 h2 = __floats2half2_rn(xv[4], xv[5]), h3 = __floats2half2_rn(xv[6], xv[7]);
-        uint4 u4;
-        u4.x = *reinterpret_cast<uint32_t*>(&h0); u4.y = *reinterpret_cast<uint32_t*>(&h1);
-        u4.z = *reinterpret_cast<uint32_t*>(&h2); u4.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>(s_b + kb * 1024 + r * 128 + ((c ^ r) << 4)) = u4;
-      }
+  for (int off = 8; off >= 1; off >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
   }
-  if (ln) {
-    float red[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) red[i] = 0.f;
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      red[r] = sx[r];
-      red[16 + r] = sxx[r];
-    }
-    s_lnred[warp * 32 + lane] = warp_transpose_reduce32(red, lane);
+  if (valid) {
+    A.x[static_cast<long long>(r) * A.d + n] = nv;
+    A.xn16[act16_off(A.R, r, n)] = __float2half_rn(nv * gain);
   }
-  fence_proxy_async_smem();
-  cons_sync();
-  // ---- one thread issues every MMA of the phase (4 per k-block), each ring unit is released by tcgen05.commit
-  if (ctid == 0) {
-    constexpr uint32_t idesc = make_idesc_f16(64, 8, false, false);
-    const uint32_t sb = smem_u32(s_b);
-    unsigned unit = rg.unit;
-    tc_fence_after();
-    for (int gi = 0; gi < n_groups; ++gi) {
-      for (int u = 0; u < units; ++u, ++unit) {
-        const int kb0 = u * g.kbu, nkb = min(g.kbu, kblocks - kb0);
-        const int st = unit % MG_NSTAGE;
-        mbar_wait(rg.full(st), (unit / MG_NSTAGE) & 1u);
-        tc_fence_after();
-        for (int i = 0; i < nkb; ++i) {
-          const uint64_t da = make_desc_sw128(rg.data0 + st * MG_STAGE_BYTES + i * g.rows_box * 128, 1024);
-          const uint64_t db = make_desc_sw128(sb + (kb0 + i) * 1024, 1024);
+  if ((lane & 15) == 0 && r < A.R) *reinterpret_cast<float2*>(A.xstat + (static_cast<long long>(blockIdx.x) * A.R + r) * 2) = make_float2(s1, s2);
+}
+
+// this warp's k-blocks of one ring unit (every 7th, starting at kbi): NMT m-tiles x 4 k-steps of ldmatrix.x4 + HMMA each,
+// branch- and predicate-free.  a_kb / b_kb: this lane's addresses for k-block kbi (A row of the swizzled box; B row with
+// the lane's row swizzle folded in), sw[ks]: the lane's swizzled 16-byte chunk of k-step ks.
+template <int NMT>
+__device__ __forceinline__ void mma_unit(float (&acc)[4][4], uint32_t a_kb, uint32_t a_step, uint32_t b_kb, uint32_t b_step,
+                                         int n_it, const uint32_t (&sw)[4]) {
+#pragma unroll 1
+  for (int it = 0; it < n_it; ++it, a_kb += a_step, b_kb += b_step) {
+    uint32_t bf[8];
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16_ss(tmem_base + static_cast<uint32_t>(gi * 8), da + 2u * k, db + 2u * k, idesc, ((kb0 + i) | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(rg.empty(st));
-      }
-    }
-    umma_commit(d_full);
-  }
-  rg.unit += static_cast<unsigned>(n_groups * units);
-  __syncwarp();
-  mbar_wait(d_full, d_count & 1u);
-  ++d_count;
-  tc_fence_after();
-  // ---- epilogue: accumulator row j of a group sits on lane 32 (j / 16) + j % 16 (M = 64): warps 0..3, lanes 0..15
-  if (warp < 4) {
-    float mean[NR], rstd[NR];
-    if (ln) {
+    for (int c = 0; c < 8; ++c) bf[c] = lds32(b_kb ^ (c << 4));
 #pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        float t1 = 0.f, t2 = 0.f;
-        for (int w = 0; w < MG_CONS_WARPS; ++w) {
-          t1 += s_lnred[w * 32 + r];
-          t2 += s_lnred[w * 32 + 16 + r];
-        }
-        mean[r] = t1 / g.K;
-        rstd[r] = rsqrtf(fmaxf(t2 / g.K - mean[r] * mean[r], 0.f) + 1e-5f);
-      }
-    }
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-    for (int gi = 0; gi < n_groups; ++gi) {
-      uint32_t acc[8];
-      tmem_ld_32x32b_x8(tmem_base + lane_off + static_cast<uint32_t>(gi * 8), acc);
-      tmem_ld_wait();
-      const int n = lo + gi * 64 + warp * 16 + lane;
-      if (lane < 16 && n < hi) {
-        const float bias = g.bias != nullptr ? __ldg(g.bias + n) : 0.f;
-        const float s2 = ln ? __ldg(g.ln_s2 + n) : 0.f;
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t af[NMT][4];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          if (r < R) {
-            float v = __uint_as_float(acc[r]);
-            if (ln) v = rstd[r] * (v - mean[r] * s2);
-            v += bias;
-            switch (g.epi) {
-              case GV_STORE:
-                g.out[static_cast<long long>(r) * g.ldo + n] = v;
-                break;
-              case GV_RESID: {
-                const float nv = s_xown[r * 16 + (n - lo)] + v;
-                s_xown[r * 16 + (n - lo)] = nv;
-                g.out[static_cast<long long>(r) * g.ldo + n] = nv;
-                break;
-              }
-              case GV_GELU:
-                g.out[static_cast<long long>(r) * g.ldo + n] = gelu_erf(v);
-                break;
-              case GV_QKV: {
-                const int d = A.d;
-                if (n < d) {
-                  g.out[static_cast<long long>(r) * g.ldo + n] = v;
-                } else {
-                  const int pos = row_pos(A, r);
-                  __half* cache = (n < 2 * d) ? ly->kcache : ly->vcache;
-                  const int e = (n < 2 * d) ? n - d : n - 2 * d;
-                  cache[(static_cast<long long>(row_slot(A, r)) * A.t_max + pos) * d + e] = __float2half_rn(v);
-                }
-                break;
-              }
-              default:
-                break;
-            }
-          }
-        }
-      }
+      for (int m = 0; m < NMT; ++m) ldmatrix_x4(a_kb + sw[ks] + m * 2048, af[m]);
+#pragma unroll
+      for (int m = 0; m < NMT; ++m) mma_m16n8k16(acc[m], af[m], bf[2 * ks], bf[2 * ks + 1]);
     }
-    tc_fence_before();
   }
 }
 
 template <int NR>
-__global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_tc_kernel(const MegaArgs A) {
-  extern __shared__ __align__(1024) uint8_t mg_smem[];
-  uint8_t* ring_data = mg_smem;
-  uint8_t* s_b = mg_smem + MT_OFF_B;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(mg_smem + MT_OFF_BARS);
-  float* s_red = reinterpret_cast<float*>(mg_smem + MT_OFF_BARS + 1024);
-  float* s_stat = s_red + MG_RED_FLOATS;
-  float* s_part = s_stat + 1056;
-  unsigned short* s_slot_tab = reinterpret_cast<unsigned short*>(reinterpret_cast<uint8_t*>(s_part) + MG_SCRATCH);
-  MegaLayer* s_ly = reinterpret_cast<MegaLayer*>(reinterpret_cast<uint8_t*>(s_slot_tab) + MG_SLOT_BYTES);
-  float* s_xown = s_stat + 784;
-  Ring rg;
-  rg.data = ring_data;
-  rg.data0 = smem_u32(ring_data);
-  rg.full0 = smem_u32(bars);
-  rg.empty0 = rg.full0 + 8 * MG_NSTAGE;
-  rg.unit = 0;
-  const uint32_t d_full = rg.full0 + 8 * (2 * MG_NSTAGE);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * MG_NSTAGE + 2);
-  const int tid = threadIdx.x;
-  if ((smem_u32(mg_smem) & 1023u) != 0) __trap();  // the swizzled operand tiles need 1024-byte alignment
-  if (tid == 0) {
-    for (int s = 0; s < MG_NSTAGE; ++s) {
-      mbar_init(rg.full(s), 1);
-      mbar_init(rg.empty(s), 1);
+__device__ __noinline__ void consume_gemv_mma(Ring& rg, const MegaArgs& A, const MegaGemv& g_mem, const MegaLayer* ly, int ctid,
+                                             uint8_t* s_b, float* s_lnstat, float* s_mpart, float* s_xown, int* s_tr,
+                                             const MmaGeom* s_geom, uint32_t xbar, unsigned& x_count) {
+  using SM = MmaSmem<NR>;
+  constexpr int NS = SM::NS;
+  const MegaGemv g = g_mem;
+  const MmaGeom mg = s_geom[g.shape];
+  if (mg.rows_pad == 0) return;  // (CTA-uniform) more CTAs than octets: nothing to stream, nothing to compute
+  const int lane = ctid & 31, warp = ctid >> 5;
+  const int R = A.R;
+  const int kblocks = g.K / 64;
+  const bool ln = g.ln_s2 != nullptr;
+  const int G = static_cast<int>(gridDim.x);
+  // ---- activations: the fp16 exchange image IS the B operand -- one bulk copy; LayerNorm inputs bring the per-CTA shares
+  //      of the row statistics along (second bulk copy on the same barrier)
+  if (ctid == 0) {
+    asm volatile("fence.proxy.async.global;" ::: "memory");  // other CTAs' generic-proxy stores (ordered by the grid barrier) -> async-proxy read
+    const uint32_t bytes = static_cast<uint32_t>(kblocks * R * 128), sbytes = ln ? static_cast<uint32_t>(G * R * 8) : 0u;
+    mbar_arrive_expect_tx(xbar, bytes + sbytes);
+    bulk_load_1d(smem_u32(s_b), g.x16, bytes, xbar);
+    if (ln) bulk_load_1d(smem_u32(s_b) + SM::STAT_OFF, A.xstat, sbytes, xbar);
+  }
+  trace_ev(A, ctid, s_tr, 1);
+  // ---- everything that does not need the activations happens while they travel: epilogue operands of this thread's
+  //      outputs (bias, LayerNorm fold term, next LayerNorm's gain) and the lane's fragment addresses
+  constexpr int NSLOT = (NR * MM_GROUP_ROWS + MG_CONS - 1) / MG_CONS;
+  const int n_groups = mg.n_full + (mg.tail ? 1 : 0);
+  const int first_rows = mg.n_full > 0 ? MM_GROUP_ROWS : mg.tail;
+  const int wsh = (n_groups == 1 && first_rows <= 16) ? 4 : 6;  // outputs of a row per 16 / 64 consecutive threads
+  float e_bias[NSLOT], e_s2[NSLOT], e_gain[NSLOT];
+  auto prefetch_epi = [&](int gi, int rows) {
+#pragma unroll
+    for (int j = 0; j < NSLOT; ++j) {
+      const int idx = ctid + j * MG_CONS;
+      const int m = idx & ((1 << wsh) - 1), n = mg.lo + gi * MM_GROUP_ROWS + m;
+      const bool ok = (idx >> wsh) < R && m < rows && n < mg.hi;
+      e_bias[j] = (ok && g.bias != nullptr) ? __ldg(g.bias + n) : 0.f;
+      e_s2[j] = (ok && ln) ? __ldg(g.ln_s2 + n) : 0.f;
+      e_gain[j] = (ok && g.next_g != nullptr) ? __ldg(g.next_g + n) : 0.f;
     }
-    mbar_init(d_full, 1);
+  };
+  prefetch_epi(0, first_rows);
+  const int gq = lane >> 2, tq = lane & 3;
+  const int brow = gq < R ? gq : R - 1;  // lanes whose activation row does not exist read the last row: their output columns are never stored
+  const uint32_t b_lane = (smem_u32(s_b) + brow * 128 + tq * 4) ^ (brow << 4);
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;
+  uint32_t sw[4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) sw[ks] = ((2 * ks + (lane >> 4)) ^ (a_row & 7)) << 4;
+  const uint32_t a_lane = rg.data0 + a_row * 128;
+  unsigned unit = rg.unit;
+  unsigned st = unit % NS, par = (unit / NS) & 1u;
+  mbar_wait(xbar, x_count & 1u);
+  ++x_count;
+  trace_ev(A, ctid, s_tr, 2);
+  for (int gi = 0; gi < n_groups; ++gi) {
+    const bool full = gi < mg.n_full;
+    const int rows = full ? MM_GROUP_ROWS : mg.tail;
+    const int n_mt = (rows + 15) >> 4;
+    const int units = full ? mg.units_full : mg.units_tail, kbu = full ? mg.kbu_full : mg.kbu_tail;
+    if (gi > 0) prefetch_epi(gi, rows);
+    float acc[4][4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[m][i] = 0.f;
+    // main loop: warp w takes the k-blocks kb = w (mod 7) of every ring unit
+    int kb_next = warp;  // this warp's next k-block of the group
+    for (int u = 0, kb0 = 0; u < units; ++u, kb0 += kbu) {
+      const int nkb = min(kbu, kblocks - kb0);
+      // every warp waits for the unit (also the ones without a k-block in it: their arrival below must not run ahead of the ring)
+      mbar_wait(rg.full(st), par);
+      if (u == 0 && gi == 0) trace_ev(A, ctid, s_tr, 3);
+      const int kbi = kb_next - kb0;
+      const int n_it = kbi < nkb ? (nkb - kbi + MG_CONS_WARPS - 1) / MG_CONS_WARPS : 0;
+      const uint32_t a_kb = a_lane + st * MG_STAGE_BYTES + kbi * rows * 128;
+      const uint32_t b_kb = b_lane + kb_next * R * 128;
+      const uint32_t a_step = MG_CONS_WARPS * rows * 128, b_step = MG_CONS_WARPS * R * 128;
+      switch (n_mt) {
+        case 1: mma_unit<1>(acc, a_kb, a_step, b_kb, b_step, n_it, sw); break;
+        case 2: mma_unit<2>(acc, a_kb, a_step, b_kb, b_step, n_it, sw); break;
+        case 3: mma_unit<3>(acc, a_kb, a_step, b_kb, b_step, n_it, sw); break;
+        default: mma_unit<4>(acc, a_kb, a_step, b_kb, b_step, n_it, sw); break;
+      }
+      kb_next += n_it * MG_CONS_WARPS;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rg.empty(st));
+      ++unit;
+      if (++st == NS) {
+        st = 0;
+        par ^= 1u;
+      }
+    }
+    trace_ev(A, ctid, s_tr, 4);
+    // ---- row statistics (first group only): quantity q = (row, sum | sum of squares) is added up over the G per-CTA
+    //      shares by 16 lanes, in a fixed order
+    if (gi == 0 && ln && ctid < 2 * R * 16) {
+      const int q = ctid >> 4, l = ctid & 15;
+      const float* stp = reinterpret_cast<const float*>(s_b + SM::STAT_OFF);
+      float t = 0.f;
+      for (int i = l; i < G; i += 16) t += stp[i * 2 * R + q];
+#pragma unroll
+      for (int off = 8; off >= 1; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+      if (l == 0) s_lnstat[q] = t;
+    }
+    // ---- the warps' partial tiles -> shared memory [warp][activation row][weight row], summed by the epilogue threads
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+      if (m < n_mt) {
+        float* p = s_mpart + (warp * 8 + 2 * tq) * MM_PART_LD + m * 16 + gq;
+        p[0] = acc[m][0];
+        p[MM_PART_LD] = acc[m][1];
+        p[8] = acc[m][2];
+        p[MM_PART_LD + 8] = acc[m][3];
+      }
+    cons_sync();
+    trace_ev(A, ctid, s_tr, 5);
+#pragma unroll
+    for (int j = 0; j < NSLOT; ++j) {
+      const int idx = ctid + j * MG_CONS;
+      const int r = idx >> wsh, m = idx & ((1 << wsh) - 1);
+      const int n = mg.lo + gi * MM_GROUP_ROWS + m;
+      const bool valid = r < R && m < rows && n < mg.hi;
+      float v = 0.f;
+      if (valid) {
+#pragma unroll
+        for (int w = 0; w < MG_CONS_WARPS; ++w) v += s_mpart[(w * 8 + r) * MM_PART_LD + m];
+        if (ln) {
+          const float mean = s_lnstat[2 * r] / g.K;
+          const float rstd = rsqrtf(fmaxf(s_lnstat[2 * r + 1] / g.K - mean * mean, 0.f) + 1e-5f);
+          v = rstd * (v - mean * e_s2[j]);
+        }
+        v += e_bias[j];
+      }
+      if (g.epi == GV_RESID) {  // (CTA-uniform; rows <= 16, one row per 16 lanes)
+        float nv = 0.f;
+        if (valid) {
+          nv = s_xown[r * 16 + (n - mg.lo)] + v;
+          s_xown[r * 16 + (n - mg.lo)] = nv;
+        }
+        if (j == 0 || (idx >> 5) * 32 < R * 16) publish_resid(A, r, n, valid, nv, e_gain[j], lane);  // (warp-uniform)
+      } else if (valid) {
+        switch (g.epi) {
+          case GV_STORE:
+            g.out[static_cast<long long>(r) * g.ldo + n] = v;
+            break;
+          case GV_GELU:
+            g.out16[act16_off(R, r, n)] = __float2half_rn(gelu_erf(v));
+            break;
+          case GV_QKV: {
+            const int d = A.d;
+            if (n < d) {
+              g.out[static_cast<long long>(r) * g.ldo + n] = v;
+            } else {
+              const int pos = row_pos(A, r);
+              __half* cache = (n < 2 * d) ? ly->kcache : ly->vcache;
+              const int e = (n < 2 * d) ? n - d : n - 2 * d;
+              cache[(static_cast<long long>(row_slot(A, r)) * A.t_max + pos) * d + e] = __float2half_rn(v);
+            }
+            break;
+          }
+          default:
+            break;
+        }
+      }
+    }
+    if (gi + 1 < n_groups) cons_sync();  // the partial tiles are rewritten by the next group
+  }
+  trace_ev(A, ctid, s_tr, 6);
+  rg.unit = unit;
+}
+
+template <int NR>
+__global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_mma_kernel(const MegaArgs A) {
+  using SM = MmaSmem<NR>;
+  constexpr int NS = SM::NS;
+  extern __shared__ __align__(1024) uint8_t mg_smem[];
+  uint8_t* s_b = mg_smem + SM::OFF_B;
+  float* s_part = reinterpret_cast<float*>(s_b);  // attention scratch: the attention phases never touch the B operand
+  float* s_mpart = reinterpret_cast<float*>(mg_smem + SM::OFF_PART);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mg_smem + SM::OFF_BARS);
+  float* s_stat = reinterpret_cast<float*>(mg_smem + SM::OFF_STAT);
+  float* s_lnstat = s_stat;  // [0, 16): row statistics of the current LayerNorm phase
+  unsigned short* s_slot_tab = reinterpret_cast<unsigned short*>(mg_smem + SM::OFF_SLOT);
+  MegaLayer* s_ly = reinterpret_cast<MegaLayer*>(mg_smem + SM::OFF_LY);
+  MmaGeom* s_geom = reinterpret_cast<MmaGeom*>(mg_smem + SM::OFF_GEOM);
+  float* s_xown = s_stat + 784;
+  int* s_tr = reinterpret_cast<int*>(s_stat + 1001);
+  Ring rg;
+  rg.data = mg_smem;
+  rg.data0 = smem_u32(mg_smem);
+  rg.full0 = smem_u32(bars);
+  rg.empty0 = rg.full0 + 8 * NS;
+  rg.unit = 0;
+  const uint32_t xbar = rg.full0 + 8 * (2 * NS);  // activation reload (bulk copy) of the GEMV phases
+  unsigned x_count = 0;
+  const int tid = threadIdx.x;
+  if ((smem_u32(mg_smem) & 1023u) != 0) __trap();  // the swizzled weight boxes need 1024-byte alignment
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(rg.full(s), 1);
+      mbar_init(rg.empty(s), MG_CONS_WARPS);
+    }
+    mbar_init(xbar, 1);
     fence_mbar_init();
   }
-  // rows of the B operand beyond the live ones are zero for the whole pass
-  for (int i = tid; i < MT_B_BYTES / 16; i += MG_THREADS) *reinterpret_cast<uint4*>(s_b + i * 16) = make_uint4(0u, 0u, 0u, 0u);
-  if (tid < 32) {
-    tmem_alloc<64>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
-    tmem_relinquish();
+  if (tid < 5) {  // geometry of the five GEMV shapes (MegaGemv::shape)
+    const int d = A.d;
+    const int Ns[5] = {3 * d, d, 4 * d, d, A.vocab.N}, Ks[5] = {d, d, d, 4 * d, d};
+    s_geom[tid] = mma_geom(Ns[tid], Ks[tid]);
   }
-  fence_proxy_async_smem();
-  tc_fence_before();
   __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
   const int L = A.n_layers;
 
   if (tid >= MG_CONS) {
@@ -1116,82 +1240,86 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_tc_kernel(const MegaAr
     if (tid == MG_CONS) {
       for (int l = 0; l < L; ++l) {
         const MegaLayer& ly = A.layers[l];
-        produce_gemv_tc(rg, ly.qkv);
-        produce_gemv_tc(rg, ly.o);
-        produce_gemv_tc(rg, ly.cq);
-        produce_cross(rg, A, ly);
-        produce_gemv_tc(rg, ly.co);
-        produce_gemv_tc(rg, ly.fc1);
-        produce_gemv_tc(rg, ly.fc2);
+        produce_gemv_mma<NS>(rg, ly.qkv, s_geom);
+        produce_gemv_mma<NS>(rg, ly.o, s_geom);
+        produce_gemv_mma<NS>(rg, ly.cq, s_geom);
+        produce_cross<NS>(rg, A, ly);
+        produce_gemv_mma<NS>(rg, ly.co, s_geom);
+        produce_gemv_mma<NS>(rg, ly.fc1, s_geom);
+        produce_gemv_mma<NS>(rg, ly.fc2, s_geom);
       }
-      if (A.with_logits) produce_gemv_tc(rg, A.vocab);
+      if (A.with_logits) produce_gemv_mma<NS>(rg, A.vocab, s_geom);
     }
-  } else {
-    // ============================== consumers
-    const int ctid = tid;
-    unsigned epoch = *A.epoch_base;
-    const unsigned epoch0 = epoch;
-    unsigned d_count = 0;
-    if (ctid == 0) *reinterpret_cast<int*>(s_stat + 1001) = 0;
-    auto prefetch_layer = [&](int l) {
-      if (ctid < static_cast<int>(sizeof(MegaLayer) / 16))
-        cp_async16(smem_u32(reinterpret_cast<uint8_t*>(s_ly) + (l & 1) * MG_LY_STRIDE) + ctid * 16,
-                   reinterpret_cast<const uint8_t*>(A.layers + l) + ctid * 16);
-    };
-    if (L > 0) prefetch_layer(0);
-    const int pos_dec = A.pf_len > 0 ? 0 : A.st->pos;
-    const int flipv = *A.flip;
-    if (A.pf_len == 0) {
-      const int task = blockIdx.x * MG_CONS_WARPS + (ctid >> 5);
-      if (task < A.R * A.H) {
-        const int* indir = (flipv ? A.indir1 : A.indir0) + static_cast<long long>(task / A.H) * A.t_max;
-        for (int t = ctid & 31; t < pos_dec; t += 32) s_slot_tab[(ctid >> 5) * 448 + t] = static_cast<unsigned short>(indir[t]);
-      }
-    }
-    cp_async_wait_all();
-    {
-      int lo, hi;
-      cta_cols(A.d, lo, hi);
-      for (int idx = ctid; idx < A.R * (hi - lo); idx += MG_CONS) {
-        const int r = idx / (hi - lo), c = idx - r * (hi - lo);
-        const float v = __half2float(A.tok_emb[static_cast<long long>(row_token(A, r)) * A.d + lo + c]) +
-                        A.pos_emb[static_cast<long long>(row_pos(A, r)) * A.d + lo + c];
-        s_xown[r * 16 + c] = v;
-        A.x[static_cast<long long>(r) * A.d + lo + c] = v;
-      }
-    }
-    grid_barrier(A, epoch, ctid, epoch0);
-    for (int l = 0; l < L; ++l) {
-      const MegaLayer& ly = *reinterpret_cast<const MegaLayer*>(reinterpret_cast<const uint8_t*>(s_ly) + (l & 1) * MG_LY_STRIDE);
-      if (l + 1 < L) prefetch_layer(l + 1);
-      consume_gemv_tc<NR>(rg, A, ly.qkv, &ly, ctid, s_b, s_red, s_xown, tmem_base, d_full, d_count);
-      grid_barrier(A, epoch, ctid, epoch0);
-      consume_self_attn(A, ly, ctid, reinterpret_cast<uint8_t*>(s_part), s_slot_tab, pos_dec, flipv);
-      grid_barrier(A, epoch, ctid, epoch0);
-      consume_gemv_tc<NR>(rg, A, ly.o, &ly, ctid, s_b, s_red, s_xown, tmem_base, d_full, d_count);
-      grid_barrier(A, epoch, ctid, epoch0);
-      consume_gemv_tc<NR>(rg, A, ly.cq, &ly, ctid, s_b, s_red, s_xown, tmem_base, d_full, d_count);
-      grid_barrier(A, epoch, ctid, epoch0);
-      consume_cross<NR, true>(rg, A, ctid, s_part, epoch + 1);
-      grid_barrier(A, epoch, ctid, epoch0);
-      consume_gemv_tc<NR>(rg, A, ly.co, &ly, ctid, s_b, s_red, s_xown, tmem_base, d_full, d_count);
-      grid_barrier(A, epoch, ctid, epoch0);
-      consume_gemv_tc<NR>(rg, A, ly.fc1, &ly, ctid, s_b, s_red, s_xown, tmem_base, d_full, d_count);
-      grid_barrier(A, epoch, ctid, epoch0);
-      consume_gemv_tc<NR>(rg, A, ly.fc2, &ly, ctid, s_b, s_red, s_xown, tmem_base, d_full, d_count);
-      cp_async_wait_all();
-      grid_barrier(A, epoch, ctid, epoch0);
-    }
-    if (A.with_logits) consume_gemv_tc<NR>(rg, A, A.vocab, nullptr, ctid, s_b, s_red, s_xown, tmem_base, d_full, d_count);
-    grid_barrier(A, epoch, ctid, epoch0);
-    if (blockIdx.x == 0 && ctid == 0) {
-      *A.epoch_base = epoch;
-      A.epoch_base[8] = epoch * gridDim.x;
+    return;
+  }
+  // ============================== consumers
+  const int ctid = tid;
+  unsigned epoch = *A.epoch_base;
+  const unsigned epoch0 = epoch;
+  if (ctid == 0) *s_tr = 0;
+  if (A.trace != nullptr && blockIdx.x == 0 && ctid == 0) A.trace[0] = globaltimer_ns();
+  auto prefetch_layer = [&](int l) {
+    if (ctid < static_cast<int>(sizeof(MegaLayer) / 16))
+      cp_async16(smem_u32(reinterpret_cast<uint8_t*>(s_ly) + (l & 1) * MG_LY_STRIDE) + ctid * 16,
+                 reinterpret_cast<const uint8_t*>(A.layers + l) + ctid * 16);
+  };
+  if (L > 0) prefetch_layer(0);
+  const int pos_dec = A.pf_len > 0 ? 0 : A.st->pos;
+  const int flipv = *A.flip;
+  if (A.pf_len == 0) {
+    const int task = blockIdx.x * MG_CONS_WARPS + (ctid >> 5);
+    if (task < A.R * A.H) {
+      const int* indir = (flipv ? A.indir1 : A.indir0) + static_cast<long long>(task / A.H) * A.t_max;
+      for (int t = ctid & 31; t < pos_dec; t += 32) s_slot_tab[(ctid >> 5) * 448 + t] = static_cast<unsigned short>(indir[t]);
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  if (tid < 32) tmem_dealloc<64>(tmem_base);
+  cp_async_wait_all();
+  {
+    // token + positional embedding: every CTA produces (and keeps) the residual-stream columns it owns and publishes them
+    // for layer 0's LayerNorm + QKV phase (16 lanes per row)
+    const MmaGeom mg = s_geom[1];
+    const float* gain0 = L > 0 ? A.layers[0].qkv.ln_g : A.vocab.ln_g;
+    for (int base = 0; base < A.R * 16; base += MG_CONS) {
+      const int idx = base + ctid;
+      const int r = idx >> 4, c = idx & 15, n = mg.lo + c;
+      const bool valid = r < A.R && n < mg.hi;
+      float v = 0.f, gain = 0.f;
+      if (valid) {
+        v = __half2float(A.tok_emb[static_cast<long long>(row_token(A, r)) * A.d + n]) + A.pos_emb[static_cast<long long>(row_pos(A, r)) * A.d + n];
+        gain = __ldg(gain0 + n);
+        s_xown[r * 16 + c] = v;
+      }
+      if ((idx >> 5) * 32 < A.R * 16) publish_resid(A, r, n, valid, v, gain, ctid & 31);  // (warp-uniform)
+    }
+  }
+  grid_barrier(A, epoch, ctid, epoch0);
+  for (int l = 0; l < L; ++l) {
+    const MegaLayer& ly = *reinterpret_cast<const MegaLayer*>(reinterpret_cast<const uint8_t*>(s_ly) + (l & 1) * MG_LY_STRIDE);
+    if (l + 1 < L) prefetch_layer(l + 1);
+    consume_gemv_mma<NR>(rg, A, ly.qkv, &ly, ctid, s_b, s_lnstat, s_mpart, s_xown, s_tr, s_geom, xbar, x_count);
+    grid_barrier(A, epoch, ctid, epoch0);
+    consume_self_attn(A, ly, ctid, reinterpret_cast<uint8_t*>(s_part), s_slot_tab, pos_dec, flipv, s_tr);
+    grid_barrier(A, epoch, ctid, epoch0);
+    consume_gemv_mma<NR>(rg, A, ly.o, &ly, ctid, s_b, s_lnstat, s_mpart, s_xown, s_tr, s_geom, xbar, x_count);
+    grid_barrier(A, epoch, ctid, epoch0);
+    consume_gemv_mma<NR>(rg, A, ly.cq, &ly, ctid, s_b, s_lnstat, s_mpart, s_xown, s_tr, s_geom, xbar, x_count);
+    grid_barrier(A, epoch, ctid, epoch0);
+    consume_cross<NR, false, NS>(rg, A, ctid, s_part, epoch + 1, s_tr);
+    grid_barrier(A, epoch, ctid, epoch0);
+    consume_gemv_mma<NR>(rg, A, ly.co, &ly, ctid, s_b, s_lnstat, s_mpart, s_xown, s_tr, s_geom, xbar, x_count);
+    grid_barrier(A, epoch, ctid, epoch0);
+    consume_gemv_mma<NR>(rg, A, ly.fc1, &ly, ctid, s_b, s_lnstat, s_mpart, s_xown, s_tr, s_geom, xbar, x_count);
+    grid_barrier(A, epoch, ctid, epoch0);
+    consume_gemv_mma<NR>(rg, A, ly.fc2, &ly, ctid, s_b, s_lnstat, s_mpart, s_xown, s_tr, s_geom, xbar, x_count);
+    cp_async_wait_all();
+    grid_barrier(A, epoch, ctid, epoch0);
+  }
+  if (A.with_logits) consume_gemv_mma<NR>(rg, A, A.vocab, nullptr, ctid, s_b, s_lnstat, s_mpart, s_xown, s_tr, s_geom, xbar, x_count);
+  grid_barrier(A, epoch, ctid, epoch0);
+  if (blockIdx.x == 0 && ctid == 0) {
+    *A.epoch_base = epoch;
+    A.epoch_base[8] = epoch * gridDim.x;
+  }
 }
 
 __global__ void chunk_major_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int N, int K, int n_chunks) {
@@ -1205,7 +1333,44 @@ __global__ void chunk_major_kernel(const __half* __restrict__ src, __half* __res
   }
 }
 
+// W [N][K] row-major -> the warp-MMA image: CTA b of a `G`-CTA pass owns the rows [lo_b, lo_b + rows_b) (whole octets, the first
+// `octets % G` CTAs one octet more); inside, groups of 64 rows, each stored [k-block][rows][64] with the 16-byte chunks of a
+// row XOR-swizzled by (row & 7).  One ring unit = a contiguous run of k-blocks = ONE bulk copy, and the bytes land in
+// shared memory exactly as ldmatrix wants them (a TMA tensor-map load per k-block was measured slower: the weights of
+// a phase were not there when its barrier opened).  Rows >= N (last octet of the vocabulary) are zero.
+__global__ void mma_image_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int N, int K, int G) {
+  const int n_oct = (N + 7) >> 3, base = n_oct / G, rem = n_oct - base * G;
+  const int big = rem * (base + 1);
+  const int kc = K >> 3;
+  const long long total = static_cast<long long>(n_oct) * 8 * kc;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / kc), c16 = static_cast<int>(i - static_cast<long long>(n) * kc);
+    const int oct = n >> 3;
+    int o0, no;
+    if (oct < big) {
+      const int b = oct / (base + 1);
+      o0 = b * (base + 1);
+      no = base + 1;
+    } else {
+      const int b = (oct - big) / base;
+      o0 = big + b * base;
+      no = base;
+    }
+    const int lo = o0 * 8, rl = n - lo, gi = rl >> 6, row = rl & 63;
+    const int rows_g = min(64, no * 8 - gi * 64);
+    const int kb = c16 >> 3, c = c16 & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (n < N) v = *reinterpret_cast<const uint4*>(src + static_cast<long long>(n) * K + c16 * 8);
+    *reinterpret_cast<uint4*>(dst + static_cast<long long>(lo + gi * 64) * K + static_cast<long long>(kb) * rows_g * 64 + row * 64 + ((c ^ (row & 7)) << 3)) = v;
+  }
+}
+
 }  // namespace
+
+void mega_mma_image(const __half* src, __half* dst, int N, int K, int grid, cudaStream_t stream) {
+  mma_image_kernel<<<1024, 256, 0, stream>>>(src, dst, N, K, grid);
+  WISB_CUDA(cudaGetLastError());
+}
 
 __global__ void ln_fold_kernel(const __half* __restrict__ w, const float* __restrict__ g, const float* __restrict__ b,
                                const float* __restrict__ bias, float* __restrict__ s2, float* __restrict__ biasf, int N, int K) {
@@ -1266,16 +1431,20 @@ void dec_pass_run(const MegaArgs& a, int num_sms, cudaStream_t stream) {
     static bool tc_attr_done[64] = {};
     bool& tc_set = tc_attr_done[dev & 63];
     if (!tc_set) {
-      WISB_CUDA(cudaFuncSetAttribute(dec_pass_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM));
-      WISB_CUDA(cudaFuncSetAttribute(dec_pass_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM));
-      WISB_CUDA(cudaFuncSetAttribute(dec_pass_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM));
+      WISB_CUDA(cudaFuncSetAttribute(dec_pass_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem<2>::TOTAL));
+      WISB_CUDA(cudaFuncSetAttribute(dec_pass_mma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem<5>::TOTAL));
+      WISB_CUDA(cudaFuncSetAttribute(dec_pass_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem<8>::TOTAL));
       tc_set = true;
     }
-    WISB_REQUIRE(a.d % 64 == 0 && 4 * a.d <= 5120, "tensor-core decoder pass: d_model <= 1280");
-    const void* fn_tc = a.R <= 2 ? reinterpret_cast<const void*>(dec_pass_tc_kernel<2>)
-                                 : a.R <= 5 ? reinterpret_cast<const void*>(dec_pass_tc_kernel<5>)
-                                            : reinterpret_cast<const void*>(dec_pass_tc_kernel<8>);
-    WISB_CUDA(cudaLaunchCooperativeKernel(fn_tc, dim3(num_sms), dim3(MG_THREADS), args, MT_SMEM, stream));
+    WISB_REQUIRE(a.d % 64 == 0 && 4 * a.d <= 5120, "warp-MMA decoder pass: d_model <= 1280");
+    WISB_REQUIRE(((a.d / 8 + num_sms - 1) / num_sms) * 8 <= 16, "warp-MMA decoder pass: too few SMs for the per-CTA residual slice");
+    if (a.R <= 2) {
+      WISB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(dec_pass_mma_kernel<2>), dim3(num_sms), dim3(MG_THREADS), args, MmaSmem<2>::TOTAL, stream));
+    } else if (a.R <= 5) {
+      WISB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(dec_pass_mma_kernel<5>), dim3(num_sms), dim3(MG_THREADS), args, MmaSmem<5>::TOTAL, stream));
+    } else {
+      WISB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(dec_pass_mma_kernel<8>), dim3(num_sms), dim3(MG_THREADS), args, MmaSmem<8>::TOTAL, stream));
+    }
     return;
   }
   const void* fn = a.R <= 2 ? reinterpret_cast<const void*>(dec_pass_kernel<2>)

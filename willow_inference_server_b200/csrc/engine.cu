@@ -127,6 +127,8 @@ struct wisb_handle {
   int plans_B = 0, plans_vmn = -1;
   // decoder workspaces
   DevBuf<float> dx, dq, dctx, dh, logits;
+  DevBuf<__half> dctx16, dh16, dxn16;
+  DevBuf<float> dxstat;  // warp-MMA pass: fp16 exchange images of the attention output and the MLP hidden rows
   DevBuf<__half> kcache, vcache;  // [L][16][448][d]
   DevBuf<uint8_t> mask_base, mask_cur;
   std::vector<int> mask_extra;
@@ -145,8 +147,7 @@ struct wisb_handle {
   std::vector<BatchLayer> bd_layers;
   GemmPlan bd_vocab;
   DevBuf<MegaLayer> mega_layers;
-  DevBuf<CUtensorMap> mega_tmaps;  // tensor-core pass: one 2-D map per decoder weight matrix (6 per layer) + the vocabulary
-  std::vector<int> mega_rows_box, mega_kbu;
+  DevBuf<__half> mega_img;  // warp-MMA pass: decoder weights as per-CTA shared-memory images (mega_mma_image)
   int mega_tc = 1;
   DevBuf<unsigned> mega_flags;
   // optional reuse of the encoder output + cross K/V between consecutive calls on identical host features
@@ -394,6 +395,10 @@ void finish_create(wisb_handle* h) {
   h->dq.ensure(R * d.d_model, true);
   h->dctx.ensure(R * d.d_model, true);
   h->dh.ensure(R * 4 * d.d_model, true);
+  h->dctx16.ensure(R * d.d_model, true);
+  h->dh16.ensure(R * 4 * d.d_model, true);
+  h->dxn16.ensure(R * d.d_model, true);
+  h->dxstat.ensure(static_cast<size_t>(h->num_sms) * R * 2, true);
   h->logits.ensure(R * d.n_vocab_pad, true);
   const size_t cache = static_cast<size_t>(d.n_dec_layers) * R * T_MAX * d.d_model;
   h->kcache.ensure(cache, true);
@@ -428,36 +433,24 @@ void finish_create(wisb_handle* h) {
       mega_chunk_major(h->dec_w[i].fc2w, h->fc2_chunked.p + per * i, d.d_model, 4 * d.d_model, h->stream);
   }
   h->cross_part.ensure(static_cast<size_t>(DEC_MAX_ROWS) * d.n_heads * 16 * MAX_BEAM * 68, true);
-  if (4 * d.d_model <= 5120) {
-    // tensor-core pass: 2-D tensor maps over the row-major decoder weights, box = 64 k x (the CTA's weight rows rounded up to
-    // whole 8-row swizzle atoms, at most 64); ring units of as many k-blocks as fit a 36 KB stage, evenly sized
-    const int n_maps = 6 * d.n_dec_layers + 1;
-    std::vector<CUtensorMap> maps(n_maps);
-    h->mega_rows_box.assign(n_maps, 0);
-    h->mega_kbu.assign(n_maps, 0);
-    auto make = [&](int idx, const __half* w, int N, int K, int rows_total) {
-      const int per = (N + h->num_sms - 1) / h->num_sms;
-      const int rows_box = round_up(per < 64 ? per : 64, 8);
-      const int kblocks = K / 64;
-      const int max_kbu = 36864 / (rows_box * 128);
-      const int n_units = (kblocks + max_kbu - 1) / max_kbu;
-      h->mega_rows_box[idx] = rows_box;
-      h->mega_kbu[idx] = (kblocks + n_units - 1) / n_units;
-      make_tmap_f16_2d(&maps[idx], w, K, rows_total, K, 64, rows_box);
-    };
-    const int dd = d.d_model;
+  if (4 * d.d_model <= 5120 && d.d_model % 64 == 0) {
+    // warp-MMA pass: a second copy of the decoder weights laid out as the shared-memory image each CTA streams
+    // (decoder_mega.cu mma_image_kernel); per layer qkv | o | cq | co | fc1 | fc2, then the vocabulary projection
+    const size_t dd = d.d_model;
+    const size_t per_layer = 14 * dd * dd;
+    const size_t vocab_rows = static_cast<size_t>((d.n_vocab + 7) / 8) * 8;
+    h->mega_img.ensure(per_layer * d.n_dec_layers + vocab_rows * dd);
     for (int i = 0; i < d.n_dec_layers; ++i) {
       const DecLayerW& w = h->dec_w[i];
-      make(6 * i + 0, w.qkvw, 3 * dd, dd, 3 * dd);
-      make(6 * i + 1, w.ow, dd, dd, dd);
-      make(6 * i + 2, w.cqw, dd, dd, dd);
-      make(6 * i + 3, w.cow, dd, dd, dd);
-      make(6 * i + 4, w.fc1w, 4 * dd, dd, 4 * dd);
-      make(6 * i + 5, w.fc2w, dd, 4 * dd, dd);
+      __half* p = h->mega_img.p + per_layer * i;
+      mega_mma_image(w.qkvw, p, 3 * d.d_model, d.d_model, h->num_sms, h->stream);
+      mega_mma_image(w.ow, p + 3 * dd * dd, d.d_model, d.d_model, h->num_sms, h->stream);
+      mega_mma_image(w.cqw, p + 4 * dd * dd, d.d_model, d.d_model, h->num_sms, h->stream);
+      mega_mma_image(w.cow, p + 5 * dd * dd, d.d_model, d.d_model, h->num_sms, h->stream);
+      mega_mma_image(w.fc1w, p + 6 * dd * dd, 4 * d.d_model, d.d_model, h->num_sms, h->stream);
+      mega_mma_image(w.fc2w, p + 10 * dd * dd, d.d_model, 4 * d.d_model, h->num_sms, h->stream);
     }
-    make(6 * d.n_dec_layers, h->H("dec.tok_emb"), d.n_vocab, dd, d.n_vocab_pad);
-    h->mega_tmaps.ensure(n_maps);
-    WISB_CUDA(cudaMemcpy(h->mega_tmaps.p, maps.data(), sizeof(CUtensorMap) * n_maps, cudaMemcpyHostToDevice));
+    mega_mma_image(h->H("dec.tok_emb"), h->mega_img.p + per_layer * d.n_dec_layers, d.n_vocab, d.d_model, h->num_sms, h->stream);
   } else {
     h->mega_tc = 0;
   }
@@ -717,12 +710,26 @@ void upload_mega_layers(wisb_handle* h, const DecodeCfg& c) {
     const __half* fc2w = (h->fc2_chunked.p && !h->mega_tc) ? h->fc2_chunked.p + static_cast<size_t>(4) * d * d * i : w.fc2w;
     set(m.fc2, fc2w, w.fc2b, nullptr, nullptr, h->dh.p, h->dx.p, d, d, 4 * d, GV_RESID);
     if (h->mega_tc) {
-      MegaGemv* gs[6] = {&m.qkv, &m.o, &m.cq, &m.co, &m.fc1, &m.fc2};
-      for (int j = 0; j < 6; ++j) {
-        gs[j]->tmap = h->mega_tmaps.p + 6 * i + j;
-        gs[j]->rows_box = h->mega_rows_box[6 * i + j];
-        gs[j]->kbu = h->mega_kbu[6 * i + j];
-      }
+      m.o.x16 = h->dctx16.p;
+      m.co.x16 = h->dctx16.p;
+      m.fc1.out16 = h->dh16.p;
+      m.fc2.x16 = h->dh16.p;
+      m.qkv.x16 = m.cq.x16 = m.fc1.x16 = h->dxn16.p;
+      m.qkv.shape = 0;
+      m.o.shape = m.cq.shape = m.co.shape = 1;
+      m.fc1.shape = 2;
+      m.fc2.shape = 3;
+      m.o.next_g = w.ln2g;
+      m.co.next_g = w.ln3g;
+      m.fc2.next_g = i + 1 < dm.n_dec_layers ? h->dec_w[i + 1].ln1g : h->F("dec.ln.g");
+      const size_t dd = d;
+      const __half* img = h->mega_img.p + 14 * dd * dd * i;
+      m.qkv.w = img;
+      m.o.w = img + 3 * dd * dd;
+      m.cq.w = img + 4 * dd * dd;
+      m.co.w = img + 5 * dd * dd;
+      m.fc1.w = img + 6 * dd * dd;
+      m.fc2.w = img + 10 * dd * dd;
     }
     m.ck = h->ckv.p + (static_cast<size_t>(i * 2 + 0) * c.B_total + c.u0) * head_block;
     m.cv = h->ckv.p + (static_cast<size_t>(i * 2 + 1) * c.B_total + c.u0) * head_block;
@@ -753,11 +760,13 @@ int enqueue_decoder_forward_mega(wisb_handle* h, const DecodeCfg& c, bool with_l
   a.vocab.K = dm.d_model;
   a.vocab.epi = GV_STORE;
   if (h->mega_tc) {
-    const int vi = 6 * dm.n_dec_layers;
-    a.vocab.tmap = h->mega_tmaps.p + vi;
-    a.vocab.rows_box = h->mega_rows_box[vi];
-    a.vocab.kbu = h->mega_kbu[vi];
+    a.vocab.w = h->mega_img.p + static_cast<size_t>(14) * dm.d_model * dm.d_model * dm.n_dec_layers;
     a.tc = 1;
+    a.ctx16 = h->dctx16.p;
+    a.xn16 = h->dxn16.p;
+    a.xstat = h->dxstat.p;
+    a.vocab.x16 = h->dxn16.p;
+    a.vocab.shape = 4;
   }
   a.with_logits = with_logits ? 1 : 0;
   a.R = c.n_utt * c.beam;
@@ -1395,8 +1404,8 @@ int wisb_set_option(wisb_handle* h, const char* key, int value) {
     else if (k == "batch_pdl") h->batch_pdl = value ? 1 : 0;
     else if (k == "mega_barrier") h->mega_barrier = value ? 1 : 0;
     else if (k == "debug_chunk") h->debug_chunk = value;
-    else if (k == "mega_tc") {  // 1: GEMV phases of the persistent pass on tcgen05, 0: the SIMT pass
-      WISB_REQUIRE(!value || h->mega_tmaps.p != nullptr, "mega_tc needs d_model <= 1280");
+    else if (k == "mega_tc" || k == "mega_mma") {  // 1: GEMV phases of the persistent pass on the warp-level tensor path, 0: the SIMT pass
+      WISB_REQUIRE(!value || h->mega_img.p != nullptr, "mega_mma needs d_model <= 1280 and a multiple of 64");
       h->mega_tc = value ? 1 : 0;
     }
     else if (k == "cross_tc") {  // 1: tcgen05 cross-attention in the batched pass, 0: the SIMT cluster kernel (cross-check)

@@ -181,6 +181,22 @@ __device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ----------------------------------------------------------------------------- warp-level MMA (skinny decoder GEMVs)
+// four 8x8 b16 matrices; lane l supplies the row address of matrix l / 8, row l % 8
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr)
+               : "memory");
+}
+// C[16x8] += A[16x16] (row-major fp16) . B[16x8] (column-major fp16), fp32 accumulate
+__device__ __forceinline__ void mma_m16n8k16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 // ----------------------------------------------------------------------------- descriptors
 // K-major operand tile in shared memory written by TMA with CU_TENSOR_MAP_SWIZZLE_128B:
 // rows of 64 fp16 (128 B), 8-row swizzle atoms of 1024 B.  (cute/arch/mma_sm100_desc.hpp SmemDescriptor:
