@@ -180,6 +180,7 @@ struct MegaArgs {
   float* q = nullptr;      // [R, d]
   float* ctx = nullptr;    // [R, d]
   __half* ctx16 = nullptr; // warp-MMA pass: attention output as an fp16 exchange image instead of `ctx`
+  __half* q16 = nullptr;   // warp-MMA pass: cross-attention queries [head][R][64] fp16, pre-scaled by 1/8
   __half* xn16 = nullptr;  // warp-MMA pass: residual rows times the next LayerNorm's gain, fp16 exchange image
   float* xstat = nullptr;  // warp-MMA pass: [CTA][R][2] per-CTA shares of the rows' (sum, sum of squares)
   const int* indir0 = nullptr;

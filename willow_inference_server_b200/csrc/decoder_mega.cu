@@ -176,7 +176,7 @@ __device__ __forceinline__ CrossGeom cross_geom(int n_utt, int H) {
   if (s < smin) s = smin;
   if (s > 16) s = 16;
   c.S = s;
-  c.KS = ((T_ENC + s - 1) / s + 7) & ~7;
+  c.KS = ((T_ENC + s - 1) / s + 15) & ~15;  // whole 16-key MMA blocks per split
   c.n_tasks = n_utt * H * s;
   return c;
 }
@@ -567,8 +567,9 @@ __device__ __noinline__ void consume_self_attn(const MegaArgs& A, const MegaLaye
 // last split of a head to arrive (atomic counter) merges the S partials into ctx.
 // kOneArrive: the ring's empty barriers count ONE arrival per stage (tensor-core pass: tcgen05.commit releases the weight
 // stages) instead of one per consumer warp
-template <int NB, bool kOneArrive = false, int NS = MG_NSTAGE>
-__device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid, float* s_part, unsigned tag, int* s_tr) {
+template <int NB, bool kOneArrive = false, int NS = MG_NSTAGE, bool kMma = false>
+__device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid, float* s_part, unsigned tag, int* s_tr,
+                                           uint32_t xbar = 0, unsigned* x_count = nullptr) {
   const int grp = ctid >> 3, gl = ctid & 7;
   constexpr int NGRP = MG_CONS / 8;  // 28
   const int d = A.d, beam = A.beam, H = A.H;
@@ -585,6 +586,109 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
     const int t0 = split * cg.KS;
     int nk = min(cg.KS, T_ENC - t0);  // keys >= 1500 (padding rows) are never touched
     if (nk < 0) nk = 0;
+    const int stK = unit % NS, stV = (unit + 1) % NS;
+    if constexpr (kMma) {
+      // ---- warp-MMA walk (FlashAttention-2 register layout): S = Q K^T with the utterance's <= 8 beams as the MMA's M rows
+      //      (rows 8..15 are zero), 16 keys per block, 7 warps over the blocks; P stays in registers as the A operand of
+      //      O += P V (V through ldmatrix.trans).  Every warp ends with (m, l, O[64]) per beam, merged below as before.
+      const int lane = ctid & 31, warp = ctid >> 5, gq = lane >> 2, tq = lane & 3;
+      // queries of the utterance's beams for this head: [head][row][64] fp16, pre-scaled (written by the cross-q phase):
+      // one bulk copy (a dependent ld.global chain after the grid barrier costs ~1 us, the bulk copy ~0.5)
+      float* s_q = s_part + 4096;
+      if (ctid == 0) {
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        mbar_arrive_expect_tx(xbar, static_cast<uint32_t>(beam * 128));
+        bulk_load_1d(smem_u32(s_q), A.q16 + (static_cast<long long>(h) * A.R + u * beam) * HEAD_DIM, static_cast<uint32_t>(beam * 128), xbar);
+      }
+      mbar_wait(xbar, *x_count & 1u);
+      ++*x_count;
+      uint32_t aq[4][2];
+      {
+        const bool row_ok = gq < beam;
+        const uint32_t qa = smem_u32(s_q) + (row_ok ? gq : 0) * 128 + tq * 4;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          aq[ks][0] = row_ok ? lds32(qa + ks * 32) : 0u;
+          aq[ks][1] = row_ok ? lds32(qa + ks * 32 + 16) : 0u;
+        }
+      }
+      float m_run = -INFINITY, l_run = 0.f;
+      float o[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[j][i] = 0.f;
+      trace_ev(A, ctid, s_tr, 11);
+      mbar_wait(ring_full0 + 8u * stK, (unit / NS) & 1u);
+      mbar_wait(ring_full0 + 8u * stV, ((unit + 1) / NS) & 1u);
+      trace_ev(A, ctid, s_tr, 12);
+      // lane's row / chunk inside a 16-key block: K (plain): matrix i = lane / 8 -> keys (i & 1) * 8.., dims 8 * (i / 2) + 32 kp..;
+      // V (transposed): matrix i -> keys (i & 1) * 8.., dims 16 jp + 8 * (i / 2)..  -- same lane address pattern
+      const uint32_t lane_off = static_cast<uint32_t>(((lane & 7) + ((lane >> 3) & 1) * 8) * 128 + (lane >> 4) * 16);
+      const uint32_t sKl = ring_data0 + stK * MG_STAGE_BYTES + lane_off, sVl = ring_data0 + stV * MG_STAGE_BYTES + lane_off;
+      for (int blk = warp; blk * 16 < nk; blk += MG_CONS_WARPS) {
+        float sc[2][4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sc[nt][i] = 0.f;
+        // (K rows are 128 bytes apart, unswizzled: ldmatrix takes 8-way bank conflicts here, 32 cycles instead of 4 -- the
+        //  layout is shared with the tcgen05 cross-attention of the batched pass, which reads it through a TMA swizzle)
+#pragma unroll
+        for (int kq = 0; kq < 4; ++kq) {  // k-step kq: dims 16 kq..16 kq + 15 of keys 0..15 of the block
+          uint32_t kf[4];
+          ldmatrix_x4(sKl + blk * 2048 + kq * 32, kf);  // {keys 0-7 | keys 8-15} x {dims +0..7 | dims +8..15}
+          const uint32_t a4[4] = {aq[kq][0], 0u, aq[kq][1], 0u};
+          mma_m16n8k16(sc[0], a4, kf[0], kf[2]);
+          mma_m16n8k16(sc[1], a4, kf[1], kf[3]);
+        }
+        // online softmax of row gq over the block's 16 keys (keys 2 tq, 2 tq + 1 of both 8-key tiles live in this lane)
+        const int k0 = blk * 16 + 2 * tq;
+        float s0 = k0 < nk ? sc[0][0] : -INFINITY, s1 = k0 + 1 < nk ? sc[0][1] : -INFINITY;
+        float s2 = k0 + 8 < nk ? sc[1][0] : -INFINITY, s3 = k0 + 9 < nk ? sc[1][1] : -INFINITY;
+        float mx = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float mn = fmaxf(m_run, mx);
+        const float al = __expf(m_run - mn);
+        const float p0 = __expf(s0 - mn), p1 = __expf(s1 - mn), p2 = __expf(s2 - mn), p3 = __expf(s3 - mn);
+        float rs = (p0 + p1) + (p2 + p3);
+        rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+        rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+        l_run = fmaf(l_run, al, rs);
+        m_run = mn;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[j][0] *= al;
+          o[j][1] *= al;
+        }
+        __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+        const uint32_t pa[4] = {*reinterpret_cast<uint32_t*>(&h01), 0u, *reinterpret_cast<uint32_t*>(&h23), 0u};
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {  // dims 16 jp..16 jp + 15
+          uint32_t vf[4];
+          ldmatrix_x4_trans(sVl + blk * 2048 + jp * 32, vf);  // {keys 0-7 | 8-15} x {dims +0..7 | +8..15}, transposed
+          mma_m16n8k16(o[2 * jp], pa, vf[0], vf[1]);
+          mma_m16n8k16(o[2 * jp + 1], pa, vf[2], vf[3]);
+        }
+      }
+      trace_ev(A, ctid, s_tr, 13);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(ring_empty0 + 8u * stK);
+        mbar_arrive(ring_empty0 + 8u * stV);
+      }
+      unit += 2;
+      if (gq < beam) {
+        float* dst = s_part + (warp * NB + gq) * 66;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(dst + 8 * j + 2 * tq) = make_float2(o[j][0], o[j][1]);
+        if (tq == 0) {
+          dst[64] = m_run;
+          dst[65] = l_run;
+        }
+      }
+    } else {
     float qv[NB][8];
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
@@ -606,7 +710,6 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
       for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
     }
     trace_ev(A, ctid, s_tr, 11);
-    const int stK = unit % NS, stV = (unit + 1) % NS;
     mbar_wait(ring_full0 + 8u * stK, (unit / NS) & 1u);
     mbar_wait(ring_full0 + 8u * stV, ((unit + 1) / NS) & 1u);
     const uint32_t sK = ring_data0 + stK * MG_STAGE_BYTES, sV = ring_data0 + stV * MG_STAGE_BYTES;
@@ -699,6 +802,7 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
           dst[65] = l[k];
         }
       }
+    }
     }
     trace_ev(A, ctid, s_tr, 14);
     cons_sync();
@@ -1165,7 +1269,8 @@ __device__ __noinline__ void consume_gemv_mma(Ring& rg, const MegaArgs& A, const
       } else if (valid) {
         switch (g.epi) {
           case GV_STORE:
-            g.out[static_cast<long long>(r) * g.ldo + n] = v;
+            if (g.out16 != nullptr) g.out16[(static_cast<long long>(n >> 6) * R + r) * HEAD_DIM + (n & 63)] = __float2half_rn(v * 0.125f);  // cross-attention query [head][row][64], pre-scaled
+            else g.out[static_cast<long long>(r) * g.ldo + n] = v;
             break;
           case GV_GELU:
             g.out16[act16_off(R, r, n)] = __float2half_rn(gelu_erf(v));
@@ -1304,7 +1409,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_mma_kernel(const MegaA
     grid_barrier(A, epoch, ctid, epoch0);
     consume_gemv_mma<NR>(rg, A, ly.cq, &ly, ctid, s_b, s_lnstat, s_mpart, s_xown, s_tr, s_geom, xbar, x_count);
     grid_barrier(A, epoch, ctid, epoch0);
-    consume_cross<NR, false, NS>(rg, A, ctid, s_part, epoch + 1, s_tr);
+    consume_cross<NR, false, NS, true>(rg, A, ctid, s_part, epoch + 1, s_tr, xbar, &x_count);
     grid_barrier(A, epoch, ctid, epoch0);
     consume_gemv_mma<NR>(rg, A, ly.co, &ly, ctid, s_b, s_lnstat, s_mpart, s_xown, s_tr, s_geom, xbar, x_count);
     grid_barrier(A, epoch, ctid, epoch0);

@@ -127,7 +127,7 @@ struct wisb_handle {
   int plans_B = 0, plans_vmn = -1;
   // decoder workspaces
   DevBuf<float> dx, dq, dctx, dh, logits;
-  DevBuf<__half> dctx16, dh16, dxn16;
+  DevBuf<__half> dctx16, dh16, dxn16, dq16;
   DevBuf<float> dxstat;  // warp-MMA pass: fp16 exchange images of the attention output and the MLP hidden rows
   DevBuf<__half> kcache, vcache;  // [L][16][448][d]
   DevBuf<uint8_t> mask_base, mask_cur;
@@ -398,6 +398,7 @@ void finish_create(wisb_handle* h) {
   h->dctx16.ensure(R * d.d_model, true);
   h->dh16.ensure(R * 4 * d.d_model, true);
   h->dxn16.ensure(R * d.d_model, true);
+  h->dq16.ensure(R * d.d_model, true);
   h->dxstat.ensure(static_cast<size_t>(h->num_sms) * R * 2, true);
   h->logits.ensure(R * d.n_vocab_pad, true);
   const size_t cache = static_cast<size_t>(d.n_dec_layers) * R * T_MAX * d.d_model;
@@ -715,6 +716,7 @@ void upload_mega_layers(wisb_handle* h, const DecodeCfg& c) {
       m.fc1.out16 = h->dh16.p;
       m.fc2.x16 = h->dh16.p;
       m.qkv.x16 = m.cq.x16 = m.fc1.x16 = h->dxn16.p;
+      m.cq.out16 = h->dq16.p;
       m.qkv.shape = 0;
       m.o.shape = m.cq.shape = m.co.shape = 1;
       m.fc1.shape = 2;
@@ -764,6 +766,7 @@ int enqueue_decoder_forward_mega(wisb_handle* h, const DecodeCfg& c, bool with_l
     a.tc = 1;
     a.ctx16 = h->dctx16.p;
     a.xn16 = h->dxn16.p;
+    a.q16 = h->dq16.p;
     a.xstat = h->dxstat.p;
     a.vocab.x16 = h->dxn16.p;
     a.vocab.shape = 4;
