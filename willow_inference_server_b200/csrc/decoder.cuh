@@ -193,12 +193,14 @@ struct MegaArgs {
   unsigned* epoch_base = nullptr;
   int barrier_mode = 0;          // 0: per-CTA epoch flags, 1: shared counter (red.release + spin)
   int tc = 0;                    // 1: GEMV phases on the warp-level tensor path (dec_pass_mma_kernel)
+  int dbg = 0;                   // diagnostics (timing experiments, results are garbage): bit 1 = stream a quarter of every weight unit
+  int trace_cta = 0, trace_layer = 0, trace_cap = 0;  // event trace: which CTA, which layer opens the window, events kept
   unsigned long long* trace = nullptr;  // optional: [2*k] = time phase k starts, [2*k+1] = time CTA 0 reached barrier k
 };
 size_t mega_flags_words();
 int mega_k_chunks(int K);
 void mega_chunk_major(const __half* src, __half* dst, int N, int K, cudaStream_t stream);
-// W [N, K] -> the image the warp-MMA pass streams with one bulk copy per ring unit ((N rounded up to 8) x K halves)
+// W [N, K] -> the image the warp-MMA pass streams with one bulk copy per ring unit (N x K halves)
 void mega_mma_image(const __half* src, __half* dst, int N, int K, int grid, cudaStream_t stream);
 // s2[n] = sum_k g[k] W[n,k];  biasf[n] = bias[n] + sum_k b[k] W[n,k]   (bias may be null)
 void mega_ln_fold(const __half* w, const float* g, const float* b, const float* bias, float* s2, float* biasf, int N, int K,

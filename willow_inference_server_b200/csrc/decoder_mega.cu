@@ -98,11 +98,14 @@ __device__ __forceinline__ int row_token(const MegaArgs& A, int r) {
 }
 
 
-// fp16 activation exchange of the warp-MMA pass: element (row r, feature k) of a [K/64 k-blocks][R rows][128 B] buffer whose
-// 16-byte chunks are XOR-swizzled by the row -- exactly the B-operand image a consumer CTA wants in shared memory, so its
-// reload is ONE bulk copy (scripts/ubench_reload: 0.7 us against 1.4 us for the ld.global reload of the same 25.6 KB)
+// fp16 activation exchange of the warp-MMA pass: element (row r, feature k) of a [K/64 k-blocks][R rows][64] buffer stored in
+// B-FRAGMENT order: inside a k-block, row r owns 4 slots of 32 bytes, slot t = (k / 2) % 4 holds the 8 words lane (g = r, t)
+// of mma.m16n8k16 feeds to the 4 k-steps {b0, b1} x 4 -- exactly the B-operand image a consumer CTA wants in shared memory.
+// Its reload is ONE bulk copy (scripts/ubench_reload: 0.7 us against 1.4 us for the ld.global reload of the same 25.6 KB)
+// and a lane fetches a whole k-block's fragments with two 16-byte loads.
 __device__ __forceinline__ long long act16_off(int R, int r, int k) {
-  return static_cast<long long>(k >> 6) * (R * 64) + r * 64 + ((((k >> 3) & 7) ^ r) << 3) + (k & 7);
+  const int kk = k & 63;
+  return static_cast<long long>(k >> 6) * (R * 64) + (r * 4 + ((kk >> 1) & 3)) * 16 + ((kk >> 4) * 2 + ((kk >> 3) & 1)) * 2 + (kk & 1);
 }
 // attention output of row r, features [col, col + 2): fp32 [R, d] (SIMT pass) or the fp16 exchange image (warp-MMA pass)
 __device__ __forceinline__ void store_ctx2(const MegaArgs& A, int r, int col, float v0, float v1) {
@@ -182,7 +185,7 @@ __device__ __forceinline__ CrossGeom cross_geom(int n_utt, int H) {
 }
 
 template <int NS = MG_NSTAGE>
-__device__ __noinline__ void produce_cross(Ring& rg, const MegaArgs& A, const MegaLayer& ly) {
+__device__ __forceinline__ void produce_cross_impl(Ring& rg, const MegaArgs& A, const MegaLayer& ly) {
   const CrossGeom cg = cross_geom(A.n_utt, A.H);
   const uint64_t pol = l2_policy_evict_first();
   for (int task = blockIdx.x; task < cg.n_tasks; task += gridDim.x) {
@@ -201,20 +204,35 @@ __device__ __noinline__ void produce_cross(Ring& rg, const MegaArgs& A, const Me
   }
 }
 
+__device__ __noinline__ void produce_cross(Ring& rg, const MegaArgs& A, const MegaLayer& ly) { produce_cross_impl<MG_NSTAGE>(rg, A, ly); }
+
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
 
-// fine-grained event trace of CTA 0 / thread 0 (debug): trace[1024 + 2 i] = event id, [.. + 1] = time
+// fine-grained event trace of thread 0 of ONE CTA over one layer (debug): (event id, SM clock) pairs collected in shared
+// memory -- a clock read and two shared stores per event, ~20 cycles, against ~130 ns for a globaltimer read plus global
+// stores -- and copied to trace[1024..] when the kernel ends.  s_tr[0] = events so far, < 0 while the window is closed.
 __device__ __forceinline__ void trace_ev(const MegaArgs& A, int ctid, int* s_tr, int id) {
-  if (A.trace != nullptr && blockIdx.x == 0 && ctid == 0) {
-    const int i = (*s_tr)++;
-    if (i < 500) {
-      A.trace[1024 + 2 * i] = static_cast<unsigned long long>(id);
-      A.trace[1024 + 2 * i + 1] = globaltimer_ns();
+  if (A.trace != nullptr && ctid == 0) {
+    const int i = s_tr[0];
+    if (i >= 0 && i < A.trace_cap) {
+      s_tr[1 + 2 * i] = id;
+      s_tr[2 + 2 * i] = static_cast<int>(clock());
+      s_tr[0] = i + 1;
     }
+  }
+}
+__device__ __forceinline__ void trace_open(const MegaArgs& A, int ctid, int* s_tr, int layer) {
+  if (A.trace != nullptr && ctid == 0 && static_cast<int>(blockIdx.x) == A.trace_cta && layer == A.trace_layer) s_tr[0] = 0;
+}
+__device__ __forceinline__ void trace_dump(const MegaArgs& A, int ctid, const int* s_tr) {
+  if (A.trace != nullptr && ctid == 0 && static_cast<int>(blockIdx.x) == A.trace_cta) {
+    const int n = s_tr[0] < 0 ? 0 : s_tr[0];
+    A.trace[1024] = static_cast<unsigned long long>(n);
+    for (int i = 0; i < 2 * n; ++i) A.trace[1025 + i] = static_cast<unsigned long long>(static_cast<unsigned>(s_tr[1 + i]));
   }
 }
 
@@ -230,7 +248,11 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 // Flag barrier: bar.sync orders the CTA's writes before thread 0's release store (cumulativity); every CTA publishes its
 // epoch in its own 128-byte line and thread i polls CTA i's line with acquire loads -- no atomics, no all-thread fences.
 __device__ __forceinline__ void grid_barrier(const MegaArgs& A, unsigned& epoch, int ctid, unsigned epoch0) {
-  if (A.trace != nullptr && blockIdx.x == 0 && ctid == 0) A.trace[2 * (epoch - epoch0) + 1] = globaltimer_ns();
+  if (A.trace != nullptr && ctid == 0) {
+    const unsigned long long t = globaltimer_ns();
+    if (blockIdx.x == 0) A.trace[2 * (epoch - epoch0) + 1] = t;
+    if (epoch - epoch0 < 264u) A.trace[2048 + blockIdx.x * 264 + (epoch - epoch0)] = t;  // arrival of every CTA at every barrier
+  }
   cons_sync();
   ++epoch;
   if (A.barrier_mode == 1) {
@@ -281,7 +303,7 @@ __device__ __noinline__ void consume_gemv(Ring& rg, const MegaArgs& A, const Meg
   const int kv = (warp - part * wpp) * 32 + lane;
   const bool active = part < n_parts && kv < n_kvec;
   const bool ln = g.ln_s2 != nullptr;
-  int* s_tr = reinterpret_cast<int*>(s_stat + 1001);
+  int* s_tr = reinterpret_cast<int*>(s_stat + 912);  // [912, 1056): event trace
   trace_ev(A, ctid, s_tr, 1);
   float* s_bias = s_stat + 16;         // [<=384] bias (LN: folded bias) of this CTA's columns
   float* s_s2 = s_stat + 400;          // [<=384] LN fold vector of this CTA's columns
@@ -568,8 +590,8 @@ __device__ __noinline__ void consume_self_attn(const MegaArgs& A, const MegaLaye
 // kOneArrive: the ring's empty barriers count ONE arrival per stage (tensor-core pass: tcgen05.commit releases the weight
 // stages) instead of one per consumer warp
 template <int NB, bool kOneArrive = false, int NS = MG_NSTAGE, bool kMma = false>
-__device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid, float* s_part, unsigned tag, int* s_tr,
-                                           uint32_t xbar = 0, unsigned* x_count = nullptr) {
+__device__ __forceinline__ void consume_cross_impl(Ring& rg, const MegaArgs& A, int ctid, float* s_part, unsigned tag, int* s_tr,
+                                                uint32_t xbar = 0, unsigned* x_count = nullptr) {
   const int grp = ctid >> 3, gl = ctid & 7;
   constexpr int NGRP = MG_CONS / 8;  // 28
   const int d = A.d, beam = A.beam, H = A.H;
@@ -842,18 +864,38 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
       }
       trace_ev(A, ctid, s_tr, 16);
       cons_sync();
-      // every load of the merge is issued before the first use: one L2 round trip for the whole fix-up
+      const float* pbase = cross_part + (static_cast<long long>(uh) * cg.S) * (MAX_BEAM * 68);
+      // warp-MMA pass: the S partial blocks of the head are contiguous -- one bulk copy into the (now idle) merge area
+      // instead of 2 x S dependent ld.global per thread
+      const uint32_t pbytes = static_cast<uint32_t>(cg.S * MAX_BEAM * 68 * 4);
+      const bool via_smem = kMma && pbytes <= 24576u;
+      if (via_smem) {
+        if (ctid == 0) {
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          mbar_arrive_expect_tx(xbar, pbytes);
+          bulk_load_1d(smem_u32(s_part), pbase, pbytes, xbar);
+        }
+        mbar_wait(xbar, *x_count & 1u);
+        ++*x_count;
+        pbase = s_part;
+      }
+      // every load of the merge is issued before the first use: one round trip for the whole fix-up
       for (int idx = ctid; idx < beam * (HEAD_DIM / 2); idx += MG_CONS) {
         const int k = idx / (HEAD_DIM / 2), e = (idx - k * (HEAD_DIM / 2)) * 2;
-        const float* pb = cross_part + (static_cast<long long>(uh) * cg.S) * (MAX_BEAM * 68) + k * 68;
+        const float* pb = pbase + k * 68;
         float2 ml[16], pv[16];
 #pragma unroll
         for (int s2 = 0; s2 < 16; ++s2) {
           ml[s2] = make_float2(-INFINITY, 0.f);
           pv[s2] = make_float2(0.f, 0.f);
           if (s2 < cg.S) {
-            ml[s2] = ldcg_f2(pb + s2 * (MAX_BEAM * 68) + 64);
-            pv[s2] = ldcg_f2(pb + s2 * (MAX_BEAM * 68) + e);
+            if (via_smem) {
+              ml[s2] = *reinterpret_cast<const float2*>(pb + s2 * (MAX_BEAM * 68) + 64);
+              pv[s2] = *reinterpret_cast<const float2*>(pb + s2 * (MAX_BEAM * 68) + e);
+            } else {
+              ml[s2] = ldcg_f2(pb + s2 * (MAX_BEAM * 68) + 64);
+              pv[s2] = ldcg_f2(pb + s2 * (MAX_BEAM * 68) + e);
+            }
           }
         }
         float mm = -INFINITY;
@@ -875,6 +917,11 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
     cons_sync();
   }
   rg.unit = unit;
+}
+
+template <int NB>
+__device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid, float* s_part, unsigned tag, int* s_tr) {
+  consume_cross_impl<NB, false, MG_NSTAGE, false>(rg, A, ctid, s_part, tag, s_tr);
 }
 
 template <int NR>
@@ -925,7 +972,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs 
   const int ctid = tid;
   unsigned epoch = *A.epoch_base;  // flags hold the epoch of the previous launch
   const unsigned epoch0 = epoch;
-  if (ctid == 0) *reinterpret_cast<int*>(s_stat + 1001) = 0;
+  int* s_tr0 = reinterpret_cast<int*>(s_stat + 912);  // [912, 1056): event trace
+  if (ctid == 0) s_tr0[0] = -1;
   if (A.trace != nullptr && blockIdx.x == 0 && ctid == 0) A.trace[0] = globaltimer_ns();
   // layer descriptors travel to shared memory one layer ahead (cp.async), so no phase starts with a global round trip
   auto prefetch_layer = [&](int l) {
@@ -962,15 +1010,16 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs 
   for (int l = 0; l < L; ++l) {
     const MegaLayer& ly = *reinterpret_cast<const MegaLayer*>(reinterpret_cast<const uint8_t*>(s_ly) + (l & 1) * MG_LY_STRIDE);
     if (l + 1 < L) prefetch_layer(l + 1);  // the other buffer was last read in layer l - 1
+    trace_open(A, ctid, s_tr0, l);
     consume_gemv<NR>(rg, A, ly.qkv, &ly, ctid, s_red, s_stat);
     grid_barrier(A, epoch, ctid, epoch0);
-    consume_self_attn(A, ly, ctid, reinterpret_cast<uint8_t*>(s_part), s_slot_tab, pos_dec, flipv, reinterpret_cast<int*>(s_stat + 1001));
+    consume_self_attn(A, ly, ctid, reinterpret_cast<uint8_t*>(s_part), s_slot_tab, pos_dec, flipv, s_tr0);
     grid_barrier(A, epoch, ctid, epoch0);
     consume_gemv<NR>(rg, A, ly.o, &ly, ctid, s_red, s_stat);
     grid_barrier(A, epoch, ctid, epoch0);
     consume_gemv<NR>(rg, A, ly.cq, &ly, ctid, s_red, s_stat);
     grid_barrier(A, epoch, ctid, epoch0);
-    consume_cross<NR>(rg, A, ctid, s_part, epoch + 1, reinterpret_cast<int*>(s_stat + 1001));  // beam <= rows <= NR; tag = a value unique to this phase
+    consume_cross<NR>(rg, A, ctid, s_part, epoch + 1, s_tr0);  // beam <= rows <= NR; tag = a value unique to this phase
     grid_barrier(A, epoch, ctid, epoch0);
     consume_gemv<NR>(rg, A, ly.co, &ly, ctid, s_red, s_stat);
     grid_barrier(A, epoch, ctid, epoch0);
@@ -983,6 +1032,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs 
   if (A.with_logits) consume_gemv<NR>(rg, A, A.vocab, nullptr, ctid, s_red, s_stat);
   // publish the final epoch for the next launch (every CTA leaves the same value behind)
   grid_barrier(A, epoch, ctid, epoch0);
+  trace_dump(A, ctid, s_tr0);
   if (blockIdx.x == 0 && ctid == 0) {
     *A.epoch_base = epoch;
     A.epoch_base[8] = epoch * gridDim.x;  // keeps the counter of the atomic barrier mode in step whatever mode ran
@@ -1029,8 +1079,10 @@ struct MmaSmem {
 constexpr int MM_GROUP_ROWS = 64;       // weight rows per accumulation group (4 m-tiles)
 constexpr int MM_PART_LD = 68;          // partial tiles [warp][8 rows][68]: conflict-free fragment stores
 
-// columns of a GEMV phase owned by this CTA, in whole octets: the first `oct % grid` CTAs own one octet more; ring units of a
-// group of `rows` weight rows: as many 64-wide k-blocks as fit a stage, evenly sized.  Computed once per kernel for the five
+// columns of a GEMV phase owned by this CTA: N / grid each, the first N % grid CTAs one more (row granularity: with whole
+// octets the twelve CTAs that owned 16 of the 1280 columns streamed twice the bytes of the others and closed every d-wide
+// phase ~0.8 us late, scripts/mega_arrivals.py); ring units of a group of `rows` weight rows: as many 64-wide k-blocks as
+// fit a stage, evenly sized.  Computed once per kernel for the five
 // GEMV shapes (qkv, d x d, fc1, fc2, vocabulary): at one warp per scheduler every instruction on a phase's critical path
 // costs ~2.5 ns, the integer divisions of this would be 0.4 us per phase.
 struct MmaGeom {
@@ -1045,12 +1097,11 @@ __device__ __forceinline__ void mma_units(int rows, int kblocks, int& units, int
 }
 __device__ __forceinline__ MmaGeom mma_geom(int N, int K) {
   MmaGeom m;
-  const int oct = (N + 7) >> 3, G = static_cast<int>(gridDim.x), b = static_cast<int>(blockIdx.x);
-  const int base = oct / G, rem = oct - base * G;
-  const int no = base + (b < rem ? 1 : 0);
-  m.lo = (b * base + min(b, rem)) * 8;
-  m.rows_pad = no * 8;
-  m.hi = min(N, m.lo + m.rows_pad);
+  const int G = static_cast<int>(gridDim.x), b = static_cast<int>(blockIdx.x);
+  const int base = N / G, rem = N - base * G;
+  m.lo = b * base + min(b, rem);
+  m.rows_pad = base + (b < rem ? 1 : 0);
+  m.hi = m.lo + m.rows_pad;
   m.n_full = m.rows_pad / MM_GROUP_ROWS;
   m.tail = m.rows_pad - m.n_full * MM_GROUP_ROWS;
   m.units_full = m.kbu_full = m.units_tail = m.kbu_tail = 0;
@@ -1060,7 +1111,7 @@ __device__ __forceinline__ MmaGeom mma_geom(int N, int K) {
 }
 
 template <int NS>
-__device__ __noinline__ void produce_gemv_mma(Ring& rg, const MegaGemv& g, const MmaGeom* s_geom) {
+__device__ __forceinline__ void produce_gemv_mma(Ring& rg, const MegaGemv& g, const MmaGeom* s_geom, int dbg) {
   const MmaGeom mg = s_geom[g.shape];
   const int n_groups = mg.n_full + (mg.tail ? 1 : 0);
   const int kblocks = g.K / 64;
@@ -1075,9 +1126,10 @@ __device__ __noinline__ void produce_gemv_mma(Ring& rg, const MegaGemv& g, const
       const int kb0 = u * kbu, nkb = min(kbu, kblocks - kb0);
       const int st = rg.unit % NS;
       mbar_wait(rg.empty(st), ((rg.unit / NS) & 1u) ^ 1u);
-      mbar_arrive_expect_tx(rg.full(st), static_cast<uint32_t>(nkb * rows * 128));
-      bulk_load_1d_hint(rg.data0 + st * MG_STAGE_BYTES, base + static_cast<long long>(kb0) * rows * 64,
-                        static_cast<uint32_t>(nkb * rows * 128), rg.full(st), pol);
+      uint32_t bytes = static_cast<uint32_t>(nkb * rows * 128);
+      if (dbg & 2) bytes = (bytes >> 2) & ~15u;  // diagnostics: a quarter of the weight traffic (results are garbage)
+      mbar_arrive_expect_tx(rg.full(st), bytes);
+      bulk_load_1d_hint(rg.data0 + st * MG_STAGE_BYTES, base + static_cast<long long>(kb0) * rows * 64, bytes, rg.full(st), pol);
       ++rg.unit;
     }
   }
@@ -1110,9 +1162,8 @@ __device__ __forceinline__ void mma_unit(float (&acc)[4][4], uint32_t a_kb, uint
                                          int n_it, const uint32_t (&sw)[4]) {
 #pragma unroll 1
   for (int it = 0; it < n_it; ++it, a_kb += a_step, b_kb += b_step) {
-    uint32_t bf[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) bf[c] = lds32(b_kb ^ (c << 4));
+    const uint4 b01 = lds128(b_kb), b23 = lds128(b_kb + 16);  // {b0, b1} of k-steps 0, 1 | 2, 3 (fragment-major image)
+    const uint32_t bf[8] = {b01.x, b01.y, b01.z, b01.w, b23.x, b23.y, b23.z, b23.w};
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       uint32_t af[NMT][4];
@@ -1124,8 +1175,196 @@ __device__ __forceinline__ void mma_unit(float (&acc)[4][4], uint32_t a_kb, uint
   }
 }
 
+// ------------------------------------------------------------------ warp-MMA pass: self-attention phase
+// task = (row, head), one warp each; task i of CTA b is  i * grid + b  (warps 0, 1 take them alternately), so at 5 rows x 20
+// heads 100 SMs work on one task each instead of 15 SMs on seven.  Per 32-key block: the K and V rows of the beam's cache
+// slots are gathered into shared memory with cp.async (16 bytes per lane, 8 lanes per row, chunks XOR-swizzled by the key so
+// that ldmatrix is conflict-free), the scores are one row of a 16 x 32 HMMA tile (rows 1..15 are zero), the probabilities
+// stay in registers as the A operand of O += P V (V through ldmatrix.trans).  The query arrives as fp16, pre-scaled, in the
+// [head][row][64] exchange layout of the QKV epilogue.
+constexpr int SA_WARPS = 2;
+__device__ __forceinline__ void consume_self_attn_mma(const MegaArgs& A, const MegaLayer& ly, int ctid, uint8_t* s_scr,
+                                                   const unsigned short* s_slot_tab, int pos_dec, int flipv, int* s_tr) {
+  const int lane = ctid & 31, warp = ctid >> 5;
+  const int d = A.d, H = A.H, G = static_cast<int>(gridDim.x);
+  const int n_tasks = A.R * H;
+  const bool pf = A.pf_len > 0;
+  trace_ev(A, ctid, s_tr, 20);
+  if (warp >= SA_WARPS) return;
+  const uint32_t sK = smem_u32(s_scr) + warp * 8192, sV = sK + 4096;
+  const unsigned short* my_slots = s_slot_tab + warp * 448;
+  const __half* kcache = ly.kcache;
+  const __half* vcache = ly.vcache;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int ld_key = lane >> 3, ld_c = lane & 7;  // gather: lane covers chunk ld_c of keys ld_key, ld_key + 4, ...
+  const uint32_t lm_off = static_cast<uint32_t>(((lane & 7) + ((lane >> 3) & 1) * 8) * 128);  // ldmatrix row of this lane
+  const int lm_c = lane >> 4;
+  for (int i = warp; i * G + static_cast<int>(blockIdx.x) < n_tasks; i += SA_WARPS) {
+    const int task = i * G + static_cast<int>(blockIdx.x);
+    const bool tab = i == warp;  // the warp's first task: its cache-slot table was staged at kernel start
+    const int r = task / H, h = task - r * H;
+    const int pos = pf ? r % A.pf_len : pos_dec;
+    const int own = row_slot(A, r);
+    const int* indir = (flipv ? A.indir1 : A.indir0) + static_cast<long long>(r) * A.t_max;
+    // query row -> A fragments (row 0 of the tile: lanes 0..3)
+    uint32_t aq[4][2];
+    {
+      const __half* qr = A.q16 + (static_cast<long long>(h) * A.R + r) * HEAD_DIM + 2 * tq;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        aq[ks][0] = gq == 0 ? __ldcg(reinterpret_cast<const unsigned*>(qr + 16 * ks)) : 0u;
+        aq[ks][1] = gq == 0 ? __ldcg(reinterpret_cast<const unsigned*>(qr + 16 * ks + 8)) : 0u;
+      }
+    }
+    float m_run = -INFINITY, l_run = 0.f;
+    float o[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[j][q] = 0.f;
+    for (int t0 = 0; t0 <= pos; t0 += 32) {
+      // ---- gather 32 keys (positions beyond `pos` re-read position `pos`: finite data, masked below)
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int key = it * 4 + ld_key;
+        const int t = min(t0 + key, pos);
+        int slot = own;
+        if (!pf && t != pos) slot = tab ? static_cast<int>(my_slots[t]) : __ldcg(indir + t);
+        const long long off = (static_cast<long long>(slot) * A.t_max + t) * d + h * HEAD_DIM + ld_c * 8;
+        const uint32_t dst = key * 128 + ((ld_c ^ (key & 7)) << 4);
+        cp_async16(sK + dst, kcache + off);
+        cp_async16(sV + dst, vcache + off);
+      }
+      cp_async_wait_all();
+      __syncwarp();
+      trace_ev(A, ctid, s_tr, 21);
+      // ---- scores: 4 tiles of 8 keys x 4 k-steps of 16 dims
+      float sc[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sc[nt][q] = 0.f;
+#pragma unroll
+      for (int kq = 0; kq < 4; ++kq) {
+        const uint32_t a4[4] = {aq[kq][0], 0u, aq[kq][1], 0u};
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {  // keys 16 half .. 16 half + 15
+          uint32_t kf[4];
+          ldmatrix_x4(sK + half * 2048 + lm_off + (((2 * kq + lm_c) ^ (lane & 7)) << 4), kf);
+          mma_m16n8k16(sc[2 * half], a4, kf[0], kf[2]);
+          mma_m16n8k16(sc[2 * half + 1], a4, kf[1], kf[3]);
+        }
+      }
+      // ---- online softmax of tile row 0 (lanes 0..3 hold keys 8 nt + 2 tq, + 1)
+      float sv[8];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int k0 = t0 + nt * 8 + 2 * tq;
+        sv[2 * nt] = k0 <= pos ? sc[nt][0] : -INFINITY;
+        sv[2 * nt + 1] = k0 + 1 <= pos ? sc[nt][1] : -INFINITY;
+      }
+      float mx = sv[0];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) mx = fmaxf(mx, sv[q]);
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float mn = fmaxf(m_run, mx);
+      const float al = __expf(m_run - mn);
+      float pr[8], rs = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        pr[q] = gq == 0 ? __expf(sv[q] - mn) : 0.f;  // rows 1..15 of the tile carry nothing
+        rs += pr[q];
+      }
+      rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+      rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+      l_run = fmaf(l_run, al, rs);
+      m_run = mn;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j][0] *= al;
+        o[j][1] *= al;
+      }
+      // ---- O += P V: 2 k-steps of 16 keys x 8 tiles of 8 dims
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        __half2 h01 = __floats2half2_rn(pr[4 * kk], pr[4 * kk + 1]), h23 = __floats2half2_rn(pr[4 * kk + 2], pr[4 * kk + 3]);
+        const uint32_t pa[4] = {*reinterpret_cast<uint32_t*>(&h01), 0u, *reinterpret_cast<uint32_t*>(&h23), 0u};
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
+          uint32_t vf[4];
+          ldmatrix_x4_trans(sV + kk * 2048 + lm_off + (((2 * jp + lm_c) ^ (lane & 7)) << 4), vf);
+          mma_m16n8k16(o[2 * jp], pa, vf[0], vf[1]);
+          mma_m16n8k16(o[2 * jp + 1], pa, vf[2], vf[3]);
+        }
+      }
+      __syncwarp();  // the next block's gather overwrites the rows
+      trace_ev(A, ctid, s_tr, 22);
+    }
+    if (gq == 0) {
+      const float inv = 1.0f / l_run;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) store_ctx2(A, r, h * HEAD_DIM + 8 * j + 2 * tq, o[j][0] * inv, o[j][1] * inv);
+    }
+    trace_ev(A, ctid, s_tr, 24);
+  }
+}
+
+// grid barrier of the warp-MMA pass (shared counter: one release-add per CTA, thread 0 spins).  The thread that sees the
+// barrier open issues the NEXT phase's activation reload at once (bulk copies onto `xbar`): the copy is the first link of
+// every phase's dependency chain, so it should not wait for the CTA-wide sync, the call and the descriptor loads.
+struct Reload {
+  const void* src = nullptr;   // fp16 exchange image -> s_b
+  uint32_t bytes = 0;
+  const void* src2 = nullptr;  // per-CTA statistic shares -> s_b + stat_off
+  uint32_t bytes2 = 0;
+};
+__device__ __forceinline__ void grid_barrier_mma(const MegaArgs& A, unsigned& epoch, int ctid, unsigned epoch0, Reload rl, uint32_t s_b_addr,
+                                              uint32_t stat_off, uint32_t xbar, int* s_tr) {
+  trace_ev(A, ctid, s_tr, 30);
+  if (A.trace != nullptr && ctid == 0) {
+    const unsigned long long t = globaltimer_ns();
+    if (blockIdx.x == 0) A.trace[2 * (epoch - epoch0) + 1] = t;
+    if (epoch - epoch0 < 264u) A.trace[2048 + blockIdx.x * 264 + (epoch - epoch0)] = t;  // arrival of every CTA at every barrier
+  }
+  cons_sync();
+  trace_ev(A, ctid, s_tr, 31);
+  ++epoch;
+  if (ctid == 0) {
+    unsigned* counter = A.epoch_base + 8;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    trace_ev(A, ctid, s_tr, 32);
+    const unsigned target = epoch * gridDim.x;
+    while (static_cast<int>(ld_acquire_gpu(counter) - target) < 0) {
+    }
+    trace_ev(A, ctid, s_tr, 33);
+    if (rl.bytes != 0) {
+      asm volatile("fence.proxy.async.global;" ::: "memory");  // other CTAs' generic-proxy stores (ordered by the barrier) -> async-proxy read
+      mbar_arrive_expect_tx(xbar, rl.bytes + rl.bytes2);
+      bulk_load_1d(s_b_addr, rl.src, rl.bytes, xbar);
+      if (rl.bytes2 != 0) bulk_load_1d(s_b_addr + stat_off, rl.src2, rl.bytes2, xbar);
+    }
+  }
+  cons_sync();
+  if (A.trace != nullptr && blockIdx.x == 0 && ctid == 0) A.trace[2 * (epoch - epoch0)] = globaltimer_ns();
+}
+// reload of a GEMV phase: its input image, plus the statistic shares when it carries a LayerNorm
+__device__ __forceinline__ Reload gemv_reload(const MegaArgs& A, const MegaGemv& g, const MmaGeom* s_geom) {
+  Reload rl;
+  if (s_geom[g.shape].rows_pad != 0) {
+    rl.src = g.x16;
+    rl.bytes = static_cast<uint32_t>((g.K / 64) * A.R * 128);
+    if (g.ln_s2 != nullptr) {
+      rl.src2 = A.xstat;
+      rl.bytes2 = static_cast<uint32_t>(gridDim.x * A.R * 8);
+    }
+  }
+  return rl;
+}
+
+
 template <int NR>
-__device__ __noinline__ void consume_gemv_mma(Ring& rg, const MegaArgs& A, const MegaGemv& g_mem, const MegaLayer* ly, int ctid,
+__device__ __forceinline__ void consume_gemv_mma(Ring& rg, const MegaArgs& A, const MegaGemv& g_mem, const MegaLayer* ly, int ctid,
                                              uint8_t* s_b, float* s_lnstat, float* s_mpart, float* s_xown, int* s_tr,
                                              const MmaGeom* s_geom, uint32_t xbar, unsigned& x_count) {
   using SM = MmaSmem<NR>;
@@ -1139,14 +1378,7 @@ __device__ __noinline__ void consume_gemv_mma(Ring& rg, const MegaArgs& A, const
   const bool ln = g.ln_s2 != nullptr;
   const int G = static_cast<int>(gridDim.x);
   // ---- activations: the fp16 exchange image IS the B operand -- one bulk copy; LayerNorm inputs bring the per-CTA shares
-  //      of the row statistics along (second bulk copy on the same barrier)
-  if (ctid == 0) {
-    asm volatile("fence.proxy.async.global;" ::: "memory");  // other CTAs' generic-proxy stores (ordered by the grid barrier) -> async-proxy read
-    const uint32_t bytes = static_cast<uint32_t>(kblocks * R * 128), sbytes = ln ? static_cast<uint32_t>(G * R * 8) : 0u;
-    mbar_arrive_expect_tx(xbar, bytes + sbytes);
-    bulk_load_1d(smem_u32(s_b), g.x16, bytes, xbar);
-    if (ln) bulk_load_1d(smem_u32(s_b) + SM::STAT_OFF, A.xstat, sbytes, xbar);
-  }
+  //      of the row statistics along; both were issued by the thread that saw the preceding grid barrier open
   trace_ev(A, ctid, s_tr, 1);
   // ---- everything that does not need the activations happens while they travel: epilogue operands of this thread's
   //      outputs (bias, LayerNorm fold term, next LayerNorm's gain) and the lane's fragment addresses
@@ -1169,7 +1401,7 @@ __device__ __noinline__ void consume_gemv_mma(Ring& rg, const MegaArgs& A, const
   prefetch_epi(0, first_rows);
   const int gq = lane >> 2, tq = lane & 3;
   const int brow = gq < R ? gq : R - 1;  // lanes whose activation row does not exist read the last row: their output columns are never stored
-  const uint32_t b_lane = (smem_u32(s_b) + brow * 128 + tq * 4) ^ (brow << 4);
+  const uint32_t b_lane = smem_u32(s_b) + (brow * 4 + tq) * 32;
   const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;
   uint32_t sw[4];
 #pragma unroll
@@ -1277,8 +1509,8 @@ __device__ __noinline__ void consume_gemv_mma(Ring& rg, const MegaArgs& A, const
             break;
           case GV_QKV: {
             const int d = A.d;
-            if (n < d) {
-              g.out[static_cast<long long>(r) * g.ldo + n] = v;
+            if (n < d) {  // self-attention query [head][row][64], pre-scaled
+              A.q16[(static_cast<long long>(n >> 6) * R + r) * HEAD_DIM + (n & 63)] = __float2half_rn(v * 0.125f);
             } else {
               const int pos = row_pos(A, r);
               __half* cache = (n < 2 * d) ? ly->kcache : ly->vcache;
@@ -1313,7 +1545,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_mma_kernel(const MegaA
   MegaLayer* s_ly = reinterpret_cast<MegaLayer*>(mg_smem + SM::OFF_LY);
   MmaGeom* s_geom = reinterpret_cast<MmaGeom*>(mg_smem + SM::OFF_GEOM);
   float* s_xown = s_stat + 784;
-  int* s_tr = reinterpret_cast<int*>(s_stat + 1001);
+  int* s_tr = reinterpret_cast<int*>(s_stat + 16);  // [16, 784): event trace (1 + 2 x 380 words)
   Ring rg;
   rg.data = mg_smem;
   rg.data0 = smem_u32(mg_smem);
@@ -1343,17 +1575,19 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_mma_kernel(const MegaA
   if (tid >= MG_CONS) {
     // ============================ producer: the static weight / KV stream of this CTA
     if (tid == MG_CONS) {
-      for (int l = 0; l < L; ++l) {
+      // (one call site per function, everything inlined: a call would park the kernel arguments and the live registers in
+      //  local memory, and every acquire of the barrier invalidates the L1 -- each access after it was an L2 round trip)
+      for (int l = 0; l <= L; ++l) {
+        if (l == L) {
+          if (A.with_logits) produce_gemv_mma<NS>(rg, A.vocab, s_geom, A.dbg);
+          break;
+        }
         const MegaLayer& ly = A.layers[l];
-        produce_gemv_mma<NS>(rg, ly.qkv, s_geom);
-        produce_gemv_mma<NS>(rg, ly.o, s_geom);
-        produce_gemv_mma<NS>(rg, ly.cq, s_geom);
-        produce_cross<NS>(rg, A, ly);
-        produce_gemv_mma<NS>(rg, ly.co, s_geom);
-        produce_gemv_mma<NS>(rg, ly.fc1, s_geom);
-        produce_gemv_mma<NS>(rg, ly.fc2, s_geom);
+        for (int j = 0; j < 7; ++j) {  // qkv, o, cross-q, [cross K/V], cross-o, fc1, fc2
+          if (j == 3) produce_cross_impl<NS>(rg, A, ly);
+          else produce_gemv_mma<NS>(rg, (&ly.qkv)[j - (j > 3)], s_geom, A.dbg);
+        }
       }
-      if (A.with_logits) produce_gemv_mma<NS>(rg, A.vocab, s_geom);
     }
     return;
   }
@@ -1361,7 +1595,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_mma_kernel(const MegaA
   const int ctid = tid;
   unsigned epoch = *A.epoch_base;
   const unsigned epoch0 = epoch;
-  if (ctid == 0) *s_tr = 0;
+  if (ctid == 0) s_tr[0] = -1;
   if (A.trace != nullptr && blockIdx.x == 0 && ctid == 0) A.trace[0] = globaltimer_ns();
   auto prefetch_layer = [&](int l) {
     if (ctid < static_cast<int>(sizeof(MegaLayer) / 16))
@@ -1371,8 +1605,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_mma_kernel(const MegaA
   if (L > 0) prefetch_layer(0);
   const int pos_dec = A.pf_len > 0 ? 0 : A.st->pos;
   const int flipv = *A.flip;
-  if (A.pf_len == 0) {
-    const int task = blockIdx.x * MG_CONS_WARPS + (ctid >> 5);
+  if (A.pf_len == 0 && (ctid >> 5) < SA_WARPS) {
+    const int task = (ctid >> 5) * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);  // consume_self_attn_mma's first task of this warp
     if (task < A.R * A.H) {
       const int* indir = (flipv ? A.indir1 : A.indir0) + static_cast<long long>(task / A.H) * A.t_max;
       for (int t = ctid & 31; t < pos_dec; t += 32) s_slot_tab[(ctid >> 5) * 448 + t] = static_cast<unsigned short>(indir[t]);
@@ -1397,30 +1631,46 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_mma_kernel(const MegaA
       if ((idx >> 5) * 32 < A.R * 16) publish_resid(A, r, n, valid, v, gain, ctid & 31);  // (warp-uniform)
     }
   }
-  grid_barrier(A, epoch, ctid, epoch0);
-  for (int l = 0; l < L; ++l) {
-    const MegaLayer& ly = *reinterpret_cast<const MegaLayer*>(reinterpret_cast<const uint8_t*>(s_ly) + (l & 1) * MG_LY_STRIDE);
-    if (l + 1 < L) prefetch_layer(l + 1);
-    consume_gemv_mma<NR>(rg, A, ly.qkv, &ly, ctid, s_b, s_lnstat, s_mpart, s_xown, s_tr, s_geom, xbar, x_count);
-    grid_barrier(A, epoch, ctid, epoch0);
-    consume_self_attn(A, ly, ctid, reinterpret_cast<uint8_t*>(s_part), s_slot_tab, pos_dec, flipv, s_tr);
-    grid_barrier(A, epoch, ctid, epoch0);
-    consume_gemv_mma<NR>(rg, A, ly.o, &ly, ctid, s_b, s_lnstat, s_mpart, s_xown, s_tr, s_geom, xbar, x_count);
-    grid_barrier(A, epoch, ctid, epoch0);
-    consume_gemv_mma<NR>(rg, A, ly.cq, &ly, ctid, s_b, s_lnstat, s_mpart, s_xown, s_tr, s_geom, xbar, x_count);
-    grid_barrier(A, epoch, ctid, epoch0);
-    consume_cross<NR, false, NS, true>(rg, A, ctid, s_part, epoch + 1, s_tr, xbar, &x_count);
-    grid_barrier(A, epoch, ctid, epoch0);
-    consume_gemv_mma<NR>(rg, A, ly.co, &ly, ctid, s_b, s_lnstat, s_mpart, s_xown, s_tr, s_geom, xbar, x_count);
-    grid_barrier(A, epoch, ctid, epoch0);
-    consume_gemv_mma<NR>(rg, A, ly.fc1, &ly, ctid, s_b, s_lnstat, s_mpart, s_xown, s_tr, s_geom, xbar, x_count);
-    grid_barrier(A, epoch, ctid, epoch0);
-    consume_gemv_mma<NR>(rg, A, ly.fc2, &ly, ctid, s_b, s_lnstat, s_mpart, s_xown, s_tr, s_geom, xbar, x_count);
-    cp_async_wait_all();
-    grid_barrier(A, epoch, ctid, epoch0);
+  const uint32_t sba = smem_u32(s_b);
+  // Phase loop with ONE inlined copy of every phase function and of the barrier (see the producer's note): layer l runs the
+  // phases 0 qkv, 1 self-attention, 2 out-proj, 3 cross-q, 4 cross-attention, 5 cross-out, 6 fc1, 7 fc2; "layer" L is the
+  // vocabulary projection alone.  The barrier that ends a phase issues the activation reload of the GEMV that follows.
+  Reload rl_next = L > 0 ? gemv_reload(A, A.layers[0].qkv, s_geom) : (A.with_logits ? gemv_reload(A, A.vocab, s_geom) : Reload());
+  for (int l = -1; l <= L; ++l) {
+    const bool vocab_layer = l == L;
+    if (vocab_layer && !A.with_logits) break;
+    const MegaLayer& ly = *reinterpret_cast<const MegaLayer*>(reinterpret_cast<const uint8_t*>(s_ly) + ((l < 0 ? 0 : l) & 1) * MG_LY_STRIDE);
+    if (l >= 0 && l + 1 < L) prefetch_layer(l + 1);
+    if (l >= 0) trace_open(A, ctid, s_tr, l);
+    const int n_ph = (l < 0 || vocab_layer) ? 1 : 8;
+    for (int ph = 0; ph < n_ph; ++ph) {
+      if (l < 0) {
+        // (the embedding phase ran above; this iteration only lends its barrier)
+      } else if (!vocab_layer && ph == 1) {
+        consume_self_attn_mma(A, ly, ctid, reinterpret_cast<uint8_t*>(s_part), s_slot_tab, pos_dec, flipv, s_tr);
+      } else if (!vocab_layer && ph == 4) {
+        consume_cross_impl<NR, false, NS, true>(rg, A, ctid, s_part, epoch + 1, s_tr, xbar, &x_count);
+      } else {
+        const MegaGemv& g = vocab_layer ? A.vocab : (&ly.qkv)[ph - (ph > 1) - (ph > 4)];
+        consume_gemv_mma<NR>(rg, A, g, &ly, ctid, s_b, s_lnstat, s_mpart, s_xown, s_tr, s_geom, xbar, x_count);
+      }
+      Reload rl = rl_next;
+      if (l >= 0) {
+        rl = Reload();
+        if (!vocab_layer) {
+          if (ph == 7) {
+            cp_async_wait_all();  // the next layer's descriptor has landed; the barrier's CTA sync publishes it
+            // (all layers share the GEMV shapes and the exchange buffers: this layer's qkv descriptor stands for the next one's)
+            rl = l + 1 < L ? gemv_reload(A, ly.qkv, s_geom) : (A.with_logits ? gemv_reload(A, A.vocab, s_geom) : Reload());
+          } else if (ph != 0 && ph != 3) {
+            rl = gemv_reload(A, (&ly.qkv)[(ph + 1) - (ph + 1 > 1) - (ph + 1 > 4)], s_geom);
+          }
+        }
+      }
+      grid_barrier_mma(A, epoch, ctid, epoch0, rl, sba, SM::STAT_OFF, xbar, s_tr);
+    }
   }
-  if (A.with_logits) consume_gemv_mma<NR>(rg, A, A.vocab, nullptr, ctid, s_b, s_lnstat, s_mpart, s_xown, s_tr, s_geom, xbar, x_count);
-  grid_barrier(A, epoch, ctid, epoch0);
+  trace_dump(A, ctid, s_tr);
   if (blockIdx.x == 0 && ctid == 0) {
     *A.epoch_base = epoch;
     A.epoch_base[8] = epoch * gridDim.x;
@@ -1438,34 +1688,30 @@ __global__ void chunk_major_kernel(const __half* __restrict__ src, __half* __res
   }
 }
 
-// W [N][K] row-major -> the warp-MMA image: CTA b of a `G`-CTA pass owns the rows [lo_b, lo_b + rows_b) (whole octets, the first
-// `octets % G` CTAs one octet more); inside, groups of 64 rows, each stored [k-block][rows][64] with the 16-byte chunks of a
-// row XOR-swizzled by (row & 7).  One ring unit = a contiguous run of k-blocks = ONE bulk copy, and the bytes land in
+// W [N][K] row-major -> the warp-MMA image: CTA b of a `G`-CTA pass owns the rows [lo_b, lo_b + rows_b) (N / G each, the first
+// N % G CTAs one more); inside, groups of 64 rows, each stored [k-block][rows][64] with the 16-byte chunks of a row
+// XOR-swizzled by (row & 7).  One ring unit = a contiguous run of k-blocks = ONE bulk copy, and the bytes land in
 // shared memory exactly as ldmatrix wants them (a TMA tensor-map load per k-block was measured slower: the weights of
-// a phase were not there when its barrier opened).  Rows >= N (last octet of the vocabulary) are zero.
+// a phase were not there when its barrier opened).
 __global__ void mma_image_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int N, int K, int G) {
-  const int n_oct = (N + 7) >> 3, base = n_oct / G, rem = n_oct - base * G;
+  const int base = N / G, rem = N - base * G;
   const int big = rem * (base + 1);
   const int kc = K >> 3;
-  const long long total = static_cast<long long>(n_oct) * 8 * kc;
+  const long long total = static_cast<long long>(N) * kc;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int n = static_cast<int>(i / kc), c16 = static_cast<int>(i - static_cast<long long>(n) * kc);
-    const int oct = n >> 3;
-    int o0, no;
-    if (oct < big) {
-      const int b = oct / (base + 1);
-      o0 = b * (base + 1);
-      no = base + 1;
+    int lo, rows;
+    if (n < big) {
+      rows = base + 1;
+      lo = (n / rows) * rows;
     } else {
-      const int b = (oct - big) / base;
-      o0 = big + b * base;
-      no = base;
+      rows = base;
+      lo = big + ((n - big) / rows) * rows;
     }
-    const int lo = o0 * 8, rl = n - lo, gi = rl >> 6, row = rl & 63;
-    const int rows_g = min(64, no * 8 - gi * 64);
+    const int rl = n - lo, gi = rl >> 6, row = rl & 63;
+    const int rows_g = min(64, rows - gi * 64);
     const int kb = c16 >> 3, c = c16 & 7;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (n < N) v = *reinterpret_cast<const uint4*>(src + static_cast<long long>(n) * K + c16 * 8);
+    const uint4 v = *reinterpret_cast<const uint4*>(src + static_cast<long long>(n) * K + c16 * 8);
     *reinterpret_cast<uint4*>(dst + static_cast<long long>(lo + gi * 64) * K + static_cast<long long>(kb) * rows_g * 64 + row * 64 + ((c ^ (row & 7)) << 3)) = v;
   }
 }
@@ -1542,7 +1788,7 @@ void dec_pass_run(const MegaArgs& a, int num_sms, cudaStream_t stream) {
       tc_set = true;
     }
     WISB_REQUIRE(a.d % 64 == 0 && 4 * a.d <= 5120, "warp-MMA decoder pass: d_model <= 1280");
-    WISB_REQUIRE(((a.d / 8 + num_sms - 1) / num_sms) * 8 <= 16, "warp-MMA decoder pass: too few SMs for the per-CTA residual slice");
+    WISB_REQUIRE((a.d + num_sms - 1) / num_sms <= 16, "warp-MMA decoder pass: too few SMs for the per-CTA residual slice");
     if (a.R <= 2) {
       WISB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(dec_pass_mma_kernel<2>), dim3(num_sms), dim3(MG_THREADS), args, MmaSmem<2>::TOTAL, stream));
     } else if (a.R <= 5) {

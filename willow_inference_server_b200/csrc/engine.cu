@@ -148,7 +148,7 @@ struct wisb_handle {
   GemmPlan bd_vocab;
   DevBuf<MegaLayer> mega_layers;
   DevBuf<__half> mega_img;  // warp-MMA pass: decoder weights as per-CTA shared-memory images (mega_mma_image)
-  int mega_tc = 1;
+  int mega_tc = 1, mega_dbg = 0;  // mega_dbg (timing experiments only): bit 0 every layer streams layer 0's weights and cross K/V (L2 resident), bit 1 a quarter of every weight unit
   DevBuf<unsigned> mega_flags;
   // optional reuse of the encoder output + cross K/V between consecutive calls on identical host features
   // (detect_language -> generate -> translate on one window, main.py:633-644, 514-547): option "encoder_cache"
@@ -161,7 +161,7 @@ struct wisb_handle {
   DevBuf<float> ln_fold;       // per LN-GEMV: s2[N] and folded bias[N] (qkv, cq, fc1 of every decoder layer, vocab)
   DevBuf<__half> fc2_chunked;  // decoder fc2 weights in chunk-major layout for the persistent pass kernel
   DevBuf<unsigned long long> mega_trace;
-  int mega_trace_on = 0;
+  int mega_trace_on = 0, mega_trace_cta = 0, mega_trace_layer = 0;
   PinBuf<MegaLayer> mega_layers_host;
   PinBuf<int> pin_i;
   PinBuf<float> pin_f;
@@ -439,7 +439,7 @@ void finish_create(wisb_handle* h) {
     // (decoder_mega.cu mma_image_kernel); per layer qkv | o | cq | co | fc1 | fc2, then the vocabulary projection
     const size_t dd = d.d_model;
     const size_t per_layer = 14 * dd * dd;
-    const size_t vocab_rows = static_cast<size_t>((d.n_vocab + 7) / 8) * 8;
+    const size_t vocab_rows = static_cast<size_t>(d.n_vocab);
     h->mega_img.ensure(per_layer * d.n_dec_layers + vocab_rows * dd);
     for (int i = 0; i < d.n_dec_layers; ++i) {
       const DecLayerW& w = h->dec_w[i];
@@ -725,7 +725,7 @@ void upload_mega_layers(wisb_handle* h, const DecodeCfg& c) {
       m.co.next_g = w.ln3g;
       m.fc2.next_g = i + 1 < dm.n_dec_layers ? h->dec_w[i + 1].ln1g : h->F("dec.ln.g");
       const size_t dd = d;
-      const __half* img = h->mega_img.p + 14 * dd * dd * i;
+      const __half* img = h->mega_img.p + 14 * dd * dd * ((h->mega_dbg & 1) ? 0 : i);
       m.qkv.w = img;
       m.o.w = img + 3 * dd * dd;
       m.cq.w = img + 4 * dd * dd;
@@ -733,8 +733,9 @@ void upload_mega_layers(wisb_handle* h, const DecodeCfg& c) {
       m.fc1.w = img + 6 * dd * dd;
       m.fc2.w = img + 10 * dd * dd;
     }
-    m.ck = h->ckv.p + (static_cast<size_t>(i * 2 + 0) * c.B_total + c.u0) * head_block;
-    m.cv = h->ckv.p + (static_cast<size_t>(i * 2 + 1) * c.B_total + c.u0) * head_block;
+    const int ikv = (h->mega_dbg & 1) ? 0 : i;
+    m.ck = h->ckv.p + (static_cast<size_t>(ikv * 2 + 0) * c.B_total + c.u0) * head_block;
+    m.cv = h->ckv.p + (static_cast<size_t>(ikv * 2 + 1) * c.B_total + c.u0) * head_block;
     m.kcache = h->kcache.p + i * layer_cache;
     m.vcache = h->vcache.p + i * layer_cache;
   }
@@ -764,6 +765,7 @@ int enqueue_decoder_forward_mega(wisb_handle* h, const DecodeCfg& c, bool with_l
   if (h->mega_tc) {
     a.vocab.w = h->mega_img.p + static_cast<size_t>(14) * dm.d_model * dm.d_model * dm.n_dec_layers;
     a.tc = 1;
+    a.dbg = h->mega_dbg;
     a.ctx16 = h->dctx16.p;
     a.xn16 = h->dxn16.p;
     a.q16 = h->dq16.p;
@@ -802,8 +804,11 @@ int enqueue_decoder_forward_mega(wisb_handle* h, const DecodeCfg& c, bool with_l
   a.epoch_base = h->mega_flags.p + 160 * 32;
   a.barrier_mode = h->mega_barrier;
   if (h->mega_trace_on) {
-    h->mega_trace.ensure(2048, true);
+    h->mega_trace.ensure(2048 + 160 * 264, true);
     a.trace = h->mega_trace.p;
+    a.trace_cta = h->mega_trace_cta;
+    a.trace_layer = h->mega_trace_layer;
+    a.trace_cap = h->mega_tc ? 380 : 70;
   }
   dec_pass_run(a, h->num_sms, h->stream);
   return 1;
@@ -1400,6 +1405,9 @@ int wisb_set_option(wisb_handle* h, const char* key, int value) {
       h->enc_valid = false;
     }
     else if (k == "mega_trace") h->mega_trace_on = value;
+    else if (k == "mega_dbg") h->mega_dbg = value;
+    else if (k == "mega_trace_cta") h->mega_trace_cta = value;
+    else if (k == "mega_trace_layer") h->mega_trace_layer = value;
     else if (k == "batch_rows") {
       WISB_REQUIRE(value >= 8 && value <= 1024, "batch_rows must be in [8, 1024]");
       h->batch_rows = value;
@@ -1675,8 +1683,8 @@ int wisb_debug_gemv_tc(wisb_handle* h, const float* x, const uint16_t* w, const 
 
 int wisb_debug_read_trace(wisb_handle* h, unsigned long long* out, int n) {
   return guarded(h, [&] {
-    WISB_REQUIRE(out != nullptr && n > 0 && n <= 2048, "bad arguments");
-    h->mega_trace.ensure(2048, true);
+    WISB_REQUIRE(out != nullptr && n > 0 && n <= 2048 + 160 * 264, "trace: at most 2048 + 160 * 264 words");
+    h->mega_trace.ensure(2048 + 160 * 264, true);
     WISB_CUDA(cudaMemcpy(out, h->mega_trace.p, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
   });
 }
