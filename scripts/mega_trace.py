@@ -23,6 +23,8 @@ h.set_option("mega_mma", 0 if "--simt" in sys.argv else 1)
 h.set_option("mega_trace", 1)
 h.set_option("mega_trace_cta", opt.get("cta", 5))
 h.set_option("mega_trace_layer", opt.get("layer", 10))
+if "dbg" in opt:
+    h.set_option("mega_dbg", opt["dbg"])
 for i in range(3):
     h.logmel(pcm.data_ptr(), off, ns, to_host=False, keep=True, pcm_on_device=True, pcm_dtype=_lib.PCM_F32, B=1)
     ids, _ = h.generate(None, prompts, bench.BEAM, 1.0, 1.0, bench.MAX_LENGTH, [dims.eot], B=1)

@@ -589,6 +589,104 @@ __device__ __noinline__ void consume_self_attn(const MegaArgs& A, const MegaLaye
 // last split of a head to arrive (atomic counter) merges the S partials into ctx.
 // kOneArrive: the ring's empty barriers count ONE arrival per stage (tensor-core pass: tcgen05.commit releases the weight
 // stages) instead of one per consumer warp
+// second half of a cross-attention task: the warps' partials (s_part: [warp][beam][64 acc, m, l]) are merged into the CTA's
+// partial for its key split, published, and split 0 of the head merges the S partials into the attention output
+template <int NB, bool kOneArrive, bool kMma>
+__device__ __forceinline__ void cross_tail(const MegaArgs& A, const CrossGeom& cg, int ctid, float* s_part, unsigned tag, int* s_tr,
+                                           uint32_t xbar, unsigned* x_count, int uh, int u, int h, int split, int beam,
+                                           uint32_t ring_empty0, int stK, int stV) {
+  float* cross_part = A.cross_part;
+  trace_ev(A, ctid, s_tr, 14);
+  cons_sync();
+  if (kOneArrive && ctid == 0) {  // every warp has left the K / V stages
+    mbar_arrive(ring_empty0 + 8u * stK);
+    mbar_arrive(ring_empty0 + 8u * stV);
+  }
+  for (int idx = ctid; idx < beam * HEAD_DIM; idx += MG_CONS) {
+    const int k = idx / HEAD_DIM, e = idx - k * HEAD_DIM;
+    float mm = -INFINITY;
+    for (int g = 0; g < MG_CONS_WARPS; ++g) mm = fmaxf(mm, s_part[(g * NB + k) * 66 + 64]);
+    float a = 0.f, ll = 0.f;
+    for (int g = 0; g < MG_CONS_WARPS; ++g) {
+      const float mg = s_part[(g * NB + k) * 66 + 64];
+      const float w = (mg == -INFINITY) ? 0.f : __expf(mg - mm);
+      a = fmaf(w, s_part[(g * NB + k) * 66 + e], a);
+      ll = fmaf(w, s_part[(g * NB + k) * 66 + 65], ll);
+    }
+    float* out = cross_part + (static_cast<long long>(uh) * cg.S + split) * (MAX_BEAM * 68) + k * 68;
+    out[e] = a;
+    if (e == 0) {
+      out[64] = mm;
+      out[65] = ll;
+    }
+  }
+  // split-K fix-up without atomics or fences on the critical path: every split publishes an epoch-tagged flag (release
+  // store by one thread after the CTA barrier); split 0 of the head polls the S flags (acquire) and merges the partials.
+  // All other CTAs go straight on to the grid barrier.
+  trace_ev(A, ctid, s_tr, 15);
+  cons_sync();
+  if (ctid == 0) st_release_gpu(A.cross_flags + (uh * 16 + split) * 32, tag);
+  if (split == 0) {
+    if (ctid < cg.S) {
+      const unsigned* f = A.cross_flags + (uh * 16 + ctid) * 32;
+      while (ld_acquire_gpu(f) != tag) {
+      }
+    }
+    trace_ev(A, ctid, s_tr, 16);
+    cons_sync();
+    const float* pbase = cross_part + (static_cast<long long>(uh) * cg.S) * (MAX_BEAM * 68);
+    // warp-MMA pass: the S partial blocks of the head are contiguous -- one bulk copy into the (now idle) merge area
+    // instead of 2 x S dependent ld.global per thread
+    const uint32_t pbytes = static_cast<uint32_t>(cg.S * MAX_BEAM * 68 * 4);
+    const bool via_smem = kMma && pbytes <= 24576u;
+    if (via_smem) {
+      if (ctid == 0) {
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        mbar_arrive_expect_tx(xbar, pbytes);
+        bulk_load_1d(smem_u32(s_part), pbase, pbytes, xbar);
+      }
+      mbar_wait(xbar, *x_count & 1u);
+      ++*x_count;
+      pbase = s_part;
+    }
+    // every load of the merge is issued before the first use: one round trip for the whole fix-up
+    for (int idx = ctid; idx < beam * (HEAD_DIM / 2); idx += MG_CONS) {
+      const int k = idx / (HEAD_DIM / 2), e = (idx - k * (HEAD_DIM / 2)) * 2;
+      const float* pb = pbase + k * 68;
+      float2 ml[16], pv[16];
+#pragma unroll
+      for (int s2 = 0; s2 < 16; ++s2) {
+        ml[s2] = make_float2(-INFINITY, 0.f);
+        pv[s2] = make_float2(0.f, 0.f);
+        if (s2 < cg.S) {
+          if (via_smem) {
+            ml[s2] = *reinterpret_cast<const float2*>(pb + s2 * (MAX_BEAM * 68) + 64);
+            pv[s2] = *reinterpret_cast<const float2*>(pb + s2 * (MAX_BEAM * 68) + e);
+          } else {
+            ml[s2] = ldcg_f2(pb + s2 * (MAX_BEAM * 68) + 64);
+            pv[s2] = ldcg_f2(pb + s2 * (MAX_BEAM * 68) + e);
+          }
+        }
+      }
+      float mm = -INFINITY;
+#pragma unroll
+      for (int s2 = 0; s2 < 16; ++s2) mm = fmaxf(mm, ml[s2].x);
+      float ax = 0.f, ay = 0.f, ll = 0.f;
+#pragma unroll
+      for (int s2 = 0; s2 < 16; ++s2) {
+        const float w = (ml[s2].x == -INFINITY) ? 0.f : __expf(ml[s2].x - mm);
+        ax = fmaf(w, pv[s2].x, ax);
+        ay = fmaf(w, pv[s2].y, ay);
+        ll = fmaf(w, ml[s2].y, ll);
+      }
+      const float inv = 1.f / ll;
+      store_ctx2(A, u * beam + k, h * HEAD_DIM + e, ax * inv, ay * inv);
+    }
+  }
+  trace_ev(A, ctid, s_tr, 17);
+  cons_sync();
+}
+
 template <int NB, bool kOneArrive = false, int NS = MG_NSTAGE, bool kMma = false>
 __device__ __forceinline__ void consume_cross_impl(Ring& rg, const MegaArgs& A, int ctid, float* s_part, unsigned tag, int* s_tr,
                                                 uint32_t xbar = 0, unsigned* x_count = nullptr) {
@@ -609,108 +707,6 @@ __device__ __forceinline__ void consume_cross_impl(Ring& rg, const MegaArgs& A, 
     int nk = min(cg.KS, T_ENC - t0);  // keys >= 1500 (padding rows) are never touched
     if (nk < 0) nk = 0;
     const int stK = unit % NS, stV = (unit + 1) % NS;
-    if constexpr (kMma) {
-      // ---- warp-MMA walk (FlashAttention-2 register layout): S = Q K^T with the utterance's <= 8 beams as the MMA's M rows
-      //      (rows 8..15 are zero), 16 keys per block, 7 warps over the blocks; P stays in registers as the A operand of
-      //      O += P V (V through ldmatrix.trans).  Every warp ends with (m, l, O[64]) per beam, merged below as before.
-      const int lane = ctid & 31, warp = ctid >> 5, gq = lane >> 2, tq = lane & 3;
-      // queries of the utterance's beams for this head: [head][row][64] fp16, pre-scaled (written by the cross-q phase):
-      // one bulk copy (a dependent ld.global chain after the grid barrier costs ~1 us, the bulk copy ~0.5)
-      float* s_q = s_part + 4096;
-      if (ctid == 0) {
-        asm volatile("fence.proxy.async.global;" ::: "memory");
-        mbar_arrive_expect_tx(xbar, static_cast<uint32_t>(beam * 128));
-        bulk_load_1d(smem_u32(s_q), A.q16 + (static_cast<long long>(h) * A.R + u * beam) * HEAD_DIM, static_cast<uint32_t>(beam * 128), xbar);
-      }
-      mbar_wait(xbar, *x_count & 1u);
-      ++*x_count;
-      uint32_t aq[4][2];
-      {
-        const bool row_ok = gq < beam;
-        const uint32_t qa = smem_u32(s_q) + (row_ok ? gq : 0) * 128 + tq * 4;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          aq[ks][0] = row_ok ? lds32(qa + ks * 32) : 0u;
-          aq[ks][1] = row_ok ? lds32(qa + ks * 32 + 16) : 0u;
-        }
-      }
-      float m_run = -INFINITY, l_run = 0.f;
-      float o[8][4];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o[j][i] = 0.f;
-      trace_ev(A, ctid, s_tr, 11);
-      mbar_wait(ring_full0 + 8u * stK, (unit / NS) & 1u);
-      mbar_wait(ring_full0 + 8u * stV, ((unit + 1) / NS) & 1u);
-      trace_ev(A, ctid, s_tr, 12);
-      // lane's row / chunk inside a 16-key block: K (plain): matrix i = lane / 8 -> keys (i & 1) * 8.., dims 8 * (i / 2) + 32 kp..;
-      // V (transposed): matrix i -> keys (i & 1) * 8.., dims 16 jp + 8 * (i / 2)..  -- same lane address pattern
-      const uint32_t lane_off = static_cast<uint32_t>(((lane & 7) + ((lane >> 3) & 1) * 8) * 128 + (lane >> 4) * 16);
-      const uint32_t sKl = ring_data0 + stK * MG_STAGE_BYTES + lane_off, sVl = ring_data0 + stV * MG_STAGE_BYTES + lane_off;
-      for (int blk = warp; blk * 16 < nk; blk += MG_CONS_WARPS) {
-        float sc[2][4];
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) sc[nt][i] = 0.f;
-        // (K rows are 128 bytes apart, unswizzled: ldmatrix takes 8-way bank conflicts here, 32 cycles instead of 4 -- the
-        //  layout is shared with the tcgen05 cross-attention of the batched pass, which reads it through a TMA swizzle)
-#pragma unroll
-        for (int kq = 0; kq < 4; ++kq) {  // k-step kq: dims 16 kq..16 kq + 15 of keys 0..15 of the block
-          uint32_t kf[4];
-          ldmatrix_x4(sKl + blk * 2048 + kq * 32, kf);  // {keys 0-7 | keys 8-15} x {dims +0..7 | dims +8..15}
-          const uint32_t a4[4] = {aq[kq][0], 0u, aq[kq][1], 0u};
-          mma_m16n8k16(sc[0], a4, kf[0], kf[2]);
-          mma_m16n8k16(sc[1], a4, kf[1], kf[3]);
-        }
-        // online softmax of row gq over the block's 16 keys (keys 2 tq, 2 tq + 1 of both 8-key tiles live in this lane)
-        const int k0 = blk * 16 + 2 * tq;
-        float s0 = k0 < nk ? sc[0][0] : -INFINITY, s1 = k0 + 1 < nk ? sc[0][1] : -INFINITY;
-        float s2 = k0 + 8 < nk ? sc[1][0] : -INFINITY, s3 = k0 + 9 < nk ? sc[1][1] : -INFINITY;
-        float mx = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        const float mn = fmaxf(m_run, mx);
-        const float al = __expf(m_run - mn);
-        const float p0 = __expf(s0 - mn), p1 = __expf(s1 - mn), p2 = __expf(s2 - mn), p3 = __expf(s3 - mn);
-        float rs = (p0 + p1) + (p2 + p3);
-        rs += __shfl_xor_sync(0xffffffffu, rs, 1);
-        rs += __shfl_xor_sync(0xffffffffu, rs, 2);
-        l_run = fmaf(l_run, al, rs);
-        m_run = mn;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          o[j][0] *= al;
-          o[j][1] *= al;
-        }
-        __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
-        const uint32_t pa[4] = {*reinterpret_cast<uint32_t*>(&h01), 0u, *reinterpret_cast<uint32_t*>(&h23), 0u};
-#pragma unroll
-        for (int jp = 0; jp < 4; ++jp) {  // dims 16 jp..16 jp + 15
-          uint32_t vf[4];
-          ldmatrix_x4_trans(sVl + blk * 2048 + jp * 32, vf);  // {keys 0-7 | 8-15} x {dims +0..7 | +8..15}, transposed
-          mma_m16n8k16(o[2 * jp], pa, vf[0], vf[1]);
-          mma_m16n8k16(o[2 * jp + 1], pa, vf[2], vf[3]);
-        }
-      }
-      trace_ev(A, ctid, s_tr, 13);
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(ring_empty0 + 8u * stK);
-        mbar_arrive(ring_empty0 + 8u * stV);
-      }
-      unit += 2;
-      if (gq < beam) {
-        float* dst = s_part + (warp * NB + gq) * 66;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(dst + 8 * j + 2 * tq) = make_float2(o[j][0], o[j][1]);
-        if (tq == 0) {
-          dst[64] = m_run;
-          dst[65] = l_run;
-        }
-      }
-    } else {
     float qv[NB][8];
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
@@ -825,96 +821,7 @@ __device__ __forceinline__ void consume_cross_impl(Ring& rg, const MegaArgs& A, 
         }
       }
     }
-    }
-    trace_ev(A, ctid, s_tr, 14);
-    cons_sync();
-    if (kOneArrive && ctid == 0) {  // every warp has left the K / V stages
-      mbar_arrive(ring_empty0 + 8u * stK);
-      mbar_arrive(ring_empty0 + 8u * stV);
-    }
-    for (int idx = ctid; idx < beam * HEAD_DIM; idx += MG_CONS) {
-      const int k = idx / HEAD_DIM, e = idx - k * HEAD_DIM;
-      float mm = -INFINITY;
-      for (int g = 0; g < MG_CONS_WARPS; ++g) mm = fmaxf(mm, s_part[(g * NB + k) * 66 + 64]);
-      float a = 0.f, ll = 0.f;
-      for (int g = 0; g < MG_CONS_WARPS; ++g) {
-        const float mg = s_part[(g * NB + k) * 66 + 64];
-        const float w = (mg == -INFINITY) ? 0.f : __expf(mg - mm);
-        a = fmaf(w, s_part[(g * NB + k) * 66 + e], a);
-        ll = fmaf(w, s_part[(g * NB + k) * 66 + 65], ll);
-      }
-      float* out = cross_part + (static_cast<long long>(uh) * cg.S + split) * (MAX_BEAM * 68) + k * 68;
-      out[e] = a;
-      if (e == 0) {
-        out[64] = mm;
-        out[65] = ll;
-      }
-    }
-    // split-K fix-up without atomics or fences on the critical path: every split publishes an epoch-tagged flag (release
-    // store by one thread after the CTA barrier); split 0 of the head polls the S flags (acquire) and merges the partials.
-    // All other CTAs go straight on to the grid barrier.
-    trace_ev(A, ctid, s_tr, 15);
-    cons_sync();
-    if (ctid == 0) st_release_gpu(A.cross_flags + (uh * 16 + split) * 32, tag);
-    if (split == 0) {
-      if (ctid < cg.S) {
-        const unsigned* f = A.cross_flags + (uh * 16 + ctid) * 32;
-        while (ld_acquire_gpu(f) != tag) {
-        }
-      }
-      trace_ev(A, ctid, s_tr, 16);
-      cons_sync();
-      const float* pbase = cross_part + (static_cast<long long>(uh) * cg.S) * (MAX_BEAM * 68);
-      // warp-MMA pass: the S partial blocks of the head are contiguous -- one bulk copy into the (now idle) merge area
-      // instead of 2 x S dependent ld.global per thread
-      const uint32_t pbytes = static_cast<uint32_t>(cg.S * MAX_BEAM * 68 * 4);
-      const bool via_smem = kMma && pbytes <= 24576u;
-      if (via_smem) {
-        if (ctid == 0) {
-          asm volatile("fence.proxy.async.global;" ::: "memory");
-          mbar_arrive_expect_tx(xbar, pbytes);
-          bulk_load_1d(smem_u32(s_part), pbase, pbytes, xbar);
-        }
-        mbar_wait(xbar, *x_count & 1u);
-        ++*x_count;
-        pbase = s_part;
-      }
-      // every load of the merge is issued before the first use: one round trip for the whole fix-up
-      for (int idx = ctid; idx < beam * (HEAD_DIM / 2); idx += MG_CONS) {
-        const int k = idx / (HEAD_DIM / 2), e = (idx - k * (HEAD_DIM / 2)) * 2;
-        const float* pb = pbase + k * 68;
-        float2 ml[16], pv[16];
-#pragma unroll
-        for (int s2 = 0; s2 < 16; ++s2) {
-          ml[s2] = make_float2(-INFINITY, 0.f);
-          pv[s2] = make_float2(0.f, 0.f);
-          if (s2 < cg.S) {
-            if (via_smem) {
-              ml[s2] = *reinterpret_cast<const float2*>(pb + s2 * (MAX_BEAM * 68) + 64);
-              pv[s2] = *reinterpret_cast<const float2*>(pb + s2 * (MAX_BEAM * 68) + e);
-            } else {
-              ml[s2] = ldcg_f2(pb + s2 * (MAX_BEAM * 68) + 64);
-              pv[s2] = ldcg_f2(pb + s2 * (MAX_BEAM * 68) + e);
-            }
-          }
-        }
-        float mm = -INFINITY;
-#pragma unroll
-        for (int s2 = 0; s2 < 16; ++s2) mm = fmaxf(mm, ml[s2].x);
-        float ax = 0.f, ay = 0.f, ll = 0.f;
-#pragma unroll
-        for (int s2 = 0; s2 < 16; ++s2) {
-          const float w = (ml[s2].x == -INFINITY) ? 0.f : __expf(ml[s2].x - mm);
-          ax = fmaf(w, pv[s2].x, ax);
-          ay = fmaf(w, pv[s2].y, ay);
-          ll = fmaf(w, ml[s2].y, ll);
-        }
-        const float inv = 1.f / ll;
-        store_ctx2(A, u * beam + k, h * HEAD_DIM + e, ax * inv, ay * inv);
-      }
-    }
-    trace_ev(A, ctid, s_tr, 17);
-    cons_sync();
+    cross_tail<NB, kOneArrive, kMma>(A, cg, ctid, s_part, tag, s_tr, xbar, x_count, uh, u, h, split, beam, ring_empty0, stK, stV);
   }
   rg.unit = unit;
 }
@@ -1062,7 +969,8 @@ template <int NR>
 struct MmaSmem {
   static constexpr int NS = NR <= 5 ? 4 : 3;                 // ring stages: a whole next phase's weights fit ahead of the consumers
   static constexpr int B_BYTES = (5120 / 64) * NR * 128;     // B operand image of the largest K (fc2): [K/64][R][128 B]
-  static constexpr int B_ALLOC = B_BYTES > MG_SCRATCH ? B_BYTES : MG_SCRATCH;
+  static constexpr int B_MIN = 32768 + 20 * NR * 128;        // fused cross phase: merge area | statistics | B operand at 32 KB
+  static constexpr int B_ALLOC = B_BYTES > B_MIN ? (B_BYTES > MG_SCRATCH ? B_BYTES : MG_SCRATCH) : (B_MIN > MG_SCRATCH ? B_MIN : MG_SCRATCH);
   static constexpr int OFF_B = NS * MG_STAGE_BYTES;          // (an m-tile's 16-row read may run 1 KB past its box: harmless)
   static constexpr int OFF_PART = OFF_B + B_ALLOC;
   static constexpr int PART_BYTES = MG_CONS_WARPS * 8 * 68 * 4;
@@ -1314,8 +1222,8 @@ __device__ __forceinline__ void consume_self_attn_mma(const MegaArgs& A, const M
 // barrier open issues the NEXT phase's activation reload at once (bulk copies onto `xbar`): the copy is the first link of
 // every phase's dependency chain, so it should not wait for the CTA-wide sync, the call and the descriptor loads.
 struct Reload {
-  const void* src = nullptr;   // fp16 exchange image -> s_b
-  uint32_t bytes = 0;
+  const void* src = nullptr;   // fp16 exchange image -> s_b + dst_off
+  uint32_t bytes = 0, dst_off = 0;
   const void* src2 = nullptr;  // per-CTA statistic shares -> s_b + stat_off
   uint32_t bytes2 = 0;
 };
@@ -1341,7 +1249,7 @@ __device__ __forceinline__ void grid_barrier_mma(const MegaArgs& A, unsigned& ep
     if (rl.bytes != 0) {
       asm volatile("fence.proxy.async.global;" ::: "memory");  // other CTAs' generic-proxy stores (ordered by the barrier) -> async-proxy read
       mbar_arrive_expect_tx(xbar, rl.bytes + rl.bytes2);
-      bulk_load_1d(s_b_addr, rl.src, rl.bytes, xbar);
+      bulk_load_1d(s_b_addr + rl.dst_off, rl.src, rl.bytes, xbar);
       if (rl.bytes2 != 0) bulk_load_1d(s_b_addr + stat_off, rl.src2, rl.bytes2, xbar);
     }
   }
@@ -1530,6 +1438,228 @@ __device__ __forceinline__ void consume_gemv_mma(Ring& rg, const MegaArgs& A, co
   rg.unit = unit;
 }
 
+// ------------------------------------------------------------------ warp-MMA pass: cross-query GEMV fused into the cross-attention
+// A grid-wide phase costs ~3.3 us of fixed latency (release fence, counter, poll, reload) whatever it computes, so the
+// LayerNorm + cross-query projection no longer has one: every key-split CTA of head h computes the head's 64 query columns
+// itself (all R rows: 64 x 1280 weights = 164 KB per CTA through the ring, the same bytes for the 7 splits of a head, so HBM
+// still reads W once and the L2 serves the rest), then walks its keys as before.  Weight image: mega_mma_image with one
+// "owner" per head.  B operand (the LayerNorm-scaled residual rows) and statistic shares: reloaded by the barrier's opener.
+constexpr int FUSED_B_OFF = 32768;  // B operand image of the fused phase inside s_b (the merge area below it stays free)
+template <int NS>
+__device__ __forceinline__ void produce_cross_fused(Ring& rg, const MegaArgs& A, const MegaLayer& ly, const MmaGeom* s_geom) {
+  const CrossGeom cg = cross_geom(A.n_utt, A.H);
+  const uint64_t pol = l2_policy_evict_first();
+  const int kblocks = A.d / 64, units = s_geom[4].units_full, kbu = s_geom[4].kbu_full;  // 64-row group, K = d
+  for (int task = blockIdx.x; task < cg.n_tasks; task += gridDim.x) {
+    const int split = task % cg.S, uh = task / cg.S;
+    const int h = uh % A.H;
+    const __half* wq = ly.cq.w + static_cast<long long>(h) * 64 * A.d;
+    for (int u = 0; u < units; ++u) {
+      const int kb0 = u * kbu, nkb = min(kbu, kblocks - kb0);
+      const int st = rg.unit % NS;
+      mbar_wait(rg.empty(st), ((rg.unit / NS) & 1u) ^ 1u);
+      mbar_arrive_expect_tx(rg.full(st), static_cast<uint32_t>(nkb * 64 * 128));
+      bulk_load_1d_hint(rg.data0 + st * MG_STAGE_BYTES, wq + static_cast<long long>(kb0) * 64 * 64, static_cast<uint32_t>(nkb * 64 * 128),
+                        rg.full(st), pol);
+      ++rg.unit;
+    }
+    const int t0 = split * cg.KS;
+    const int nk = min(cg.KS, T_ENC_PAD - t0);
+    const long long off = (static_cast<long long>(uh) * T_ENC_PAD + t0) * HEAD_DIM;
+    for (int kv = 0; kv < 2; ++kv) {
+      const int st = rg.unit % NS;
+      mbar_wait(rg.empty(st), ((rg.unit / NS) & 1u) ^ 1u);
+      mbar_arrive_expect_tx(rg.full(st), static_cast<uint32_t>(nk * HEAD_DIM * 2));
+      bulk_load_1d_hint(rg.data0 + st * MG_STAGE_BYTES, (kv == 0 ? ly.ck : ly.cv) + off, static_cast<uint32_t>(nk * HEAD_DIM * 2), rg.full(st), pol);
+      ++rg.unit;
+    }
+  }
+}
+
+template <int NB, int NS>
+__device__ __forceinline__ void consume_cross_fused(Ring& rg, const MegaArgs& A, const MegaLayer& ly, int ctid, uint8_t* s_b, float* s_mpart,
+                                                    float* s_lnstat, int* s_tr, const MmaGeom* s_geom, uint32_t xbar, unsigned& x_count,
+                                                    unsigned tag, int stat_off) {
+  float* s_part = reinterpret_cast<float*>(s_b);  // attention scratch: merge area, queries at +4096 floats
+  float* s_q = s_part + 4096;
+  const MegaGemv g = ly.cq;
+  const int lane = ctid & 31, warp = ctid >> 5, gq = lane >> 2, tq = lane & 3;
+  const int R = A.R, d = A.d, beam = A.beam, H = A.H, G = static_cast<int>(gridDim.x);
+  const CrossGeom cg = cross_geom(A.n_utt, H);
+  const int kblocks = d / 64, units = s_geom[4].units_full, kbu = s_geom[4].kbu_full;
+  const uint32_t ring_data0 = rg.data0, ring_full0 = rg.full0, ring_empty0 = rg.empty0;
+  unsigned unit = rg.unit;
+  trace_ev(A, ctid, s_tr, 10);
+  // the LayerNorm-scaled residual rows + statistic shares (issued by the thread that saw the barrier open)
+  mbar_wait(xbar, x_count & 1u);
+  ++x_count;
+  if (ctid < 2 * R * 16) {  // row statistics, as in consume_gemv_mma
+    const int q = ctid >> 4, l = ctid & 15;
+    const float* stp = reinterpret_cast<const float*>(s_b + stat_off);
+    float t = 0.f;
+    for (int i = l; i < G; i += 16) t += stp[i * 2 * R + q];
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+    if (l == 0) s_lnstat[q] = t;
+  }
+  const int brow = gq < R ? gq : R - 1;
+  const uint32_t b_lane = smem_u32(s_b) + FUSED_B_OFF + (brow * 4 + tq) * 32;
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;
+  uint32_t sw[4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) sw[ks] = ((2 * ks + (lane >> 4)) ^ (a_row & 7)) << 4;
+  const uint32_t a_lane = ring_data0 + a_row * 128;
+  constexpr int NSLOT = (NB * 64 + MG_CONS - 1) / MG_CONS;
+  for (int task = blockIdx.x; task < cg.n_tasks; task += gridDim.x) {
+    const int split = task % cg.S, uh = task / cg.S;
+    const int u = uh / H, h = uh - u * H;
+    const int t0 = split * cg.KS;
+    int nk = min(cg.KS, T_ENC - t0);  // keys >= 1500 (padding rows) are never touched
+    if (nk < 0) nk = 0;
+    // ---- cross-query projection of head h: 64 weight rows x all R rows
+    float e_bias[NSLOT], e_s2[NSLOT];
+#pragma unroll
+    for (int j = 0; j < NSLOT; ++j) {
+      const int idx = ctid + j * MG_CONS;
+      const bool ok = (idx >> 6) < R;
+      e_bias[j] = ok ? __ldg(g.bias + h * 64 + (idx & 63)) : 0.f;
+      e_s2[j] = ok ? __ldg(g.ln_s2 + h * 64 + (idx & 63)) : 0.f;
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[m][i] = 0.f;
+    int kb_next = warp;
+    for (int uu = 0, kb0 = 0; uu < units; ++uu, kb0 += kbu, ++unit) {
+      const int nkb = min(kbu, kblocks - kb0);
+      const unsigned st = unit % NS;
+      mbar_wait(ring_full0 + 8u * st, (unit / NS) & 1u);
+      const int kbi = kb_next - kb0;
+      const int n_it = kbi < nkb ? (nkb - kbi + MG_CONS_WARPS - 1) / MG_CONS_WARPS : 0;
+      mma_unit<4>(acc, a_lane + st * MG_STAGE_BYTES + kbi * 64 * 128, MG_CONS_WARPS * 64 * 128, b_lane + kb_next * R * 128,
+                  MG_CONS_WARPS * R * 128, n_it, sw);
+      kb_next += n_it * MG_CONS_WARPS;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ring_empty0 + 8u * st);
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      float* p = s_mpart + (warp * 8 + 2 * tq) * MM_PART_LD + m * 16 + gq;
+      p[0] = acc[m][0];
+      p[MM_PART_LD] = acc[m][1];
+      p[8] = acc[m][2];
+      p[MM_PART_LD + 8] = acc[m][3];
+    }
+    cons_sync();
+#pragma unroll
+    for (int j = 0; j < NSLOT; ++j) {
+      const int idx = ctid + j * MG_CONS;
+      const int r = idx >> 6, c = idx & 63;
+      const int rl = r - u * beam;  // row inside the utterance
+      if (r < R && rl >= 0 && rl < beam) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < MG_CONS_WARPS; ++w) v += s_mpart[(w * 8 + r) * MM_PART_LD + c];
+        const float mean = s_lnstat[2 * r] / d;
+        const float rstd = rsqrtf(fmaxf(s_lnstat[2 * r + 1] / d - mean * mean, 0.f) + 1e-5f);
+        v = rstd * (v - mean * e_s2[j]) + e_bias[j];
+        reinterpret_cast<__half*>(s_q)[rl * 64 + c] = __float2half_rn(v * 0.125f);  // pre-scaled query
+      }
+    }
+    cons_sync();
+    trace_ev(A, ctid, s_tr, 11);
+    // ---- warp-MMA walk (FlashAttention-2 register layout): S = Q K^T with the utterance's <= 8 beams as the MMA's M rows
+    //      (rows 8..15 are zero), 16 keys per block, 7 warps over the blocks; P stays in registers as the A operand of
+    //      O += P V (V through ldmatrix.trans).  Every warp ends with (m, l, O[64]) per beam, merged in cross_tail.
+    const int stK = unit % NS, stV = (unit + 1) % NS;
+    uint32_t aq[4][2];
+    {
+      const bool row_ok = gq < beam;
+      const uint32_t qa = smem_u32(s_q) + (row_ok ? gq : 0) * 128 + tq * 4;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        aq[ks][0] = row_ok ? lds32(qa + ks * 32) : 0u;
+        aq[ks][1] = row_ok ? lds32(qa + ks * 32 + 16) : 0u;
+      }
+    }
+    float m_run = -INFINITY, l_run = 0.f;
+    float o[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[j][i] = 0.f;
+    mbar_wait(ring_full0 + 8u * stK, (unit / NS) & 1u);
+    mbar_wait(ring_full0 + 8u * stV, ((unit + 1) / NS) & 1u);
+    trace_ev(A, ctid, s_tr, 12);
+    const uint32_t lane_off = static_cast<uint32_t>(((lane & 7) + ((lane >> 3) & 1) * 8) * 128 + (lane >> 4) * 16);
+    const uint32_t sKl = ring_data0 + stK * MG_STAGE_BYTES + lane_off, sVl = ring_data0 + stV * MG_STAGE_BYTES + lane_off;
+    for (int blk = warp; blk * 16 < nk; blk += MG_CONS_WARPS) {
+      float sc[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sc[nt][i] = 0.f;
+      // (K rows are 128 bytes apart, unswizzled: ldmatrix takes 8-way bank conflicts here, 32 cycles instead of 4 -- the
+      //  layout is shared with the tcgen05 cross-attention of the batched pass, which reads it through a TMA swizzle)
+#pragma unroll
+      for (int kq = 0; kq < 4; ++kq) {
+        uint32_t kf[4];
+        ldmatrix_x4(sKl + blk * 2048 + kq * 32, kf);
+        const uint32_t a4[4] = {aq[kq][0], 0u, aq[kq][1], 0u};
+        mma_m16n8k16(sc[0], a4, kf[0], kf[2]);
+        mma_m16n8k16(sc[1], a4, kf[1], kf[3]);
+      }
+      const int k0 = blk * 16 + 2 * tq;
+      float s0 = k0 < nk ? sc[0][0] : -INFINITY, s1 = k0 + 1 < nk ? sc[0][1] : -INFINITY;
+      float s2 = k0 + 8 < nk ? sc[1][0] : -INFINITY, s3 = k0 + 9 < nk ? sc[1][1] : -INFINITY;
+      float mx = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float mn = fmaxf(m_run, mx);
+      const float al = __expf(m_run - mn);
+      const float p0 = __expf(s0 - mn), p1 = __expf(s1 - mn), p2 = __expf(s2 - mn), p3 = __expf(s3 - mn);
+      float rs = (p0 + p1) + (p2 + p3);
+      rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+      rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+      l_run = fmaf(l_run, al, rs);
+      m_run = mn;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j][0] *= al;
+        o[j][1] *= al;
+      }
+      __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+      const uint32_t pa[4] = {*reinterpret_cast<uint32_t*>(&h01), 0u, *reinterpret_cast<uint32_t*>(&h23), 0u};
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        uint32_t vf[4];
+        ldmatrix_x4_trans(sVl + blk * 2048 + jp * 32, vf);
+        mma_m16n8k16(o[2 * jp], pa, vf[0], vf[1]);
+        mma_m16n8k16(o[2 * jp + 1], pa, vf[2], vf[3]);
+      }
+    }
+    trace_ev(A, ctid, s_tr, 13);
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(ring_empty0 + 8u * stK);
+      mbar_arrive(ring_empty0 + 8u * stV);
+    }
+    unit += 2;
+    if (gq < beam) {
+      float* dst = s_part + (warp * NB + gq) * 66;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(dst + 8 * j + 2 * tq) = make_float2(o[j][0], o[j][1]);
+      if (tq == 0) {
+        dst[64] = m_run;
+        dst[65] = l_run;
+      }
+    }
+    cross_tail<NB, false, true>(A, cg, ctid, s_part, tag, s_tr, xbar, &x_count, uh, u, h, split, beam, ring_empty0, stK, stV);
+  }
+  rg.unit = unit;
+}
+
 template <int NR>
 __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_mma_kernel(const MegaArgs A) {
   using SM = MmaSmem<NR>;
@@ -1583,9 +1713,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_mma_kernel(const MegaA
           break;
         }
         const MegaLayer& ly = A.layers[l];
-        for (int j = 0; j < 7; ++j) {  // qkv, o, cross-q, [cross K/V], cross-o, fc1, fc2
-          if (j == 3) produce_cross_impl<NS>(rg, A, ly);
-          else produce_gemv_mma<NS>(rg, (&ly.qkv)[j - (j > 3)], s_geom, A.dbg);
+        for (int j = 0; j < 6; ++j) {  // qkv, o, [cross-q of the task's head + cross K/V], cross-o, fc1, fc2
+          if (j == 2) produce_cross_fused<NS>(rg, A, ly, s_geom);
+          else produce_gemv_mma<NS>(rg, (&ly.qkv)[j], s_geom, A.dbg);  // (index 2, the cross-query GEMV, is the fused phase's)
         }
       }
     }
@@ -1633,8 +1763,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_mma_kernel(const MegaA
   }
   const uint32_t sba = smem_u32(s_b);
   // Phase loop with ONE inlined copy of every phase function and of the barrier (see the producer's note): layer l runs the
-  // phases 0 qkv, 1 self-attention, 2 out-proj, 3 cross-q, 4 cross-attention, 5 cross-out, 6 fc1, 7 fc2; "layer" L is the
-  // vocabulary projection alone.  The barrier that ends a phase issues the activation reload of the GEMV that follows.
+  // phases 0 qkv, 1 self-attention, 2 out-proj, 3 cross-attention (with its query projection), 4 cross-out, 5 fc1, 6 fc2;
+  // "layer" L is the vocabulary projection alone.  The barrier that ends a phase issues the activation reload of the GEMV that follows.
   Reload rl_next = L > 0 ? gemv_reload(A, A.layers[0].qkv, s_geom) : (A.with_logits ? gemv_reload(A, A.vocab, s_geom) : Reload());
   for (int l = -1; l <= L; ++l) {
     const bool vocab_layer = l == L;
@@ -1642,28 +1772,34 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_mma_kernel(const MegaA
     const MegaLayer& ly = *reinterpret_cast<const MegaLayer*>(reinterpret_cast<const uint8_t*>(s_ly) + ((l < 0 ? 0 : l) & 1) * MG_LY_STRIDE);
     if (l >= 0 && l + 1 < L) prefetch_layer(l + 1);
     if (l >= 0) trace_open(A, ctid, s_tr, l);
-    const int n_ph = (l < 0 || vocab_layer) ? 1 : 8;
+    const int n_ph = (l < 0 || vocab_layer) ? 1 : 7;
     for (int ph = 0; ph < n_ph; ++ph) {
       if (l < 0) {
         // (the embedding phase ran above; this iteration only lends its barrier)
       } else if (!vocab_layer && ph == 1) {
         consume_self_attn_mma(A, ly, ctid, reinterpret_cast<uint8_t*>(s_part), s_slot_tab, pos_dec, flipv, s_tr);
-      } else if (!vocab_layer && ph == 4) {
-        consume_cross_impl<NR, false, NS, true>(rg, A, ctid, s_part, epoch + 1, s_tr, xbar, &x_count);
+      } else if (!vocab_layer && ph == 3) {
+        consume_cross_fused<NR, NS>(rg, A, ly, ctid, s_b, s_mpart, s_lnstat, s_tr, s_geom, xbar, x_count, epoch + 1, SM::STAT_OFF);
       } else {
-        const MegaGemv& g = vocab_layer ? A.vocab : (&ly.qkv)[ph - (ph > 1) - (ph > 4)];
+        const MegaGemv& g = vocab_layer ? A.vocab : (&ly.qkv)[ph == 0 ? 0 : (ph == 2 ? 1 : ph - 1)];
         consume_gemv_mma<NR>(rg, A, g, &ly, ctid, s_b, s_lnstat, s_mpart, s_xown, s_tr, s_geom, xbar, x_count);
       }
       Reload rl = rl_next;
       if (l >= 0) {
         rl = Reload();
         if (!vocab_layer) {
-          if (ph == 7) {
+          if (ph == 6) {
             cp_async_wait_all();  // the next layer's descriptor has landed; the barrier's CTA sync publishes it
             // (all layers share the GEMV shapes and the exchange buffers: this layer's qkv descriptor stands for the next one's)
             rl = l + 1 < L ? gemv_reload(A, ly.qkv, s_geom) : (A.with_logits ? gemv_reload(A, A.vocab, s_geom) : Reload());
-          } else if (ph != 0 && ph != 3) {
-            rl = gemv_reload(A, (&ly.qkv)[(ph + 1) - (ph + 1 > 1) - (ph + 1 > 4)], s_geom);
+          } else if (ph == 2) {  // next: cross-attention with its own query projection (B operand above the merge area)
+            rl.src = ly.cq.x16;  // (every CTA: also the ones that own no column of a d-wide GEMV wait for it)
+            rl.bytes = static_cast<uint32_t>((A.d / 64) * A.R * 128);
+            rl.src2 = A.xstat;
+            rl.bytes2 = static_cast<uint32_t>(gridDim.x * A.R * 8);
+            rl.dst_off = FUSED_B_OFF;
+          } else if (ph != 0) {  // 1 -> out-proj, 3 -> cross-out, 4 -> fc1, 5 -> fc2
+            rl = gemv_reload(A, (&ly.qkv)[ph == 1 ? 1 : ph], s_geom);
           }
         }
       }

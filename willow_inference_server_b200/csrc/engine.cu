@@ -446,7 +446,7 @@ void finish_create(wisb_handle* h) {
       __half* p = h->mega_img.p + per_layer * i;
       mega_mma_image(w.qkvw, p, 3 * d.d_model, d.d_model, h->num_sms, h->stream);
       mega_mma_image(w.ow, p + 3 * dd * dd, d.d_model, d.d_model, h->num_sms, h->stream);
-      mega_mma_image(w.cqw, p + 4 * dd * dd, d.d_model, d.d_model, h->num_sms, h->stream);
+      mega_mma_image(w.cqw, p + 4 * dd * dd, d.d_model, d.d_model, d.n_heads, h->stream);  // head-major: the cross phase projects its own queries
       mega_mma_image(w.cow, p + 5 * dd * dd, d.d_model, d.d_model, h->num_sms, h->stream);
       mega_mma_image(w.fc1w, p + 6 * dd * dd, 4 * d.d_model, d.d_model, h->num_sms, h->stream);
       mega_mma_image(w.fc2w, p + 10 * dd * dd, d.d_model, 4 * d.d_model, h->num_sms, h->stream);
