@@ -17,6 +17,7 @@ struct DecState {
   int gen_step;   // 0-based index of the token being generated (valid once pos >= prompt_len - 1)
   int n_done;     // utterances finished
   int all_done;   // n_done == n_utt
+  int ticket;     // CTAs of search_tail_kernel that finished this step's bookkeeping (the last one advances the step)
 };
 
 enum GemvEpi : int {

@@ -833,6 +833,7 @@ __device__ __noinline__ void consume_cross(Ring& rg, const MegaArgs& A, int ctid
 
 template <int NR>
 __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs A) {
+  if (A.pf_len == 0 && A.st->all_done) return;  // a step enqueued ahead of the host's poll (every thread of every CTA leaves)
   extern __shared__ __align__(1024) uint8_t mg_smem[];
   uint8_t* ring_data = mg_smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(mg_smem + MG_NSTAGE * MG_STAGE_BYTES);
@@ -1662,6 +1663,7 @@ __device__ __forceinline__ void consume_cross_fused(Ring& rg, const MegaArgs& A,
 
 template <int NR>
 __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_mma_kernel(const MegaArgs A) {
+  if (A.pf_len == 0 && A.st->all_done) return;  // a step enqueued ahead of the host's poll (every thread of every CTA leaves)
   using SM = MmaSmem<NR>;
   constexpr int NS = SM::NS;
   extern __shared__ __align__(1024) uint8_t mg_smem[];

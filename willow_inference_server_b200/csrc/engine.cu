@@ -162,6 +162,7 @@ struct wisb_handle {
   DevBuf<__half> fc2_chunked;  // decoder fc2 weights in chunk-major layout for the persistent pass kernel
   DevBuf<unsigned long long> mega_trace;
   int mega_trace_on = 0, mega_trace_cta = 0, mega_trace_layer = 0;
+  cudaEvent_t ev_flag[2] = {nullptr, nullptr};  // decode loop: `all_done` copies of the last two steps
   PinBuf<MegaLayer> mega_layers_host;
   PinBuf<int> pin_i;
   PinBuf<float> pin_f;
@@ -960,14 +961,34 @@ int decode_pass(wisb_handle* h, const DecodeCfg& c, const int32_t* prompts, int3
       }
     }
     const int fwd = h->decoder_mega ? 1 : 1 + 8 * h->dims.n_dec_layers + 1;
-    const int per_step = fwd + 4;
+    const int per_step = fwd + 2;
     h->launches += (c.prompt_len - 1) * (fwd + 1);
     volatile int* flag = h->pin_i.p;
-    *flag = 0;
+    flag[0] = flag[1] = 0;
+    // persistent-pass path with a poll every step: step gs + 1 is enqueued BEFORE the host waits for step gs's `all_done`
+    // word (the kernels of a step that turns out to be superfluous leave at once on the device flag), so neither the
+    // launch latency of the cooperative kernel nor the host's wake-up sits between two steps
+    const bool ahead = h->decoder_mega && h->decode_poll == 1;
+    if (ahead && h->ev_flag[0] == nullptr) {
+      WISB_CUDA(cudaEventCreateWithFlags(&h->ev_flag[0], cudaEventDisableTiming));
+      WISB_CUDA(cudaEventCreateWithFlags(&h->ev_flag[1], cudaEventDisableTiming));
+    }
     for (int gs = 0; gs < c.max_new; ++gs) {
       if (g) WISB_CUDA(cudaGraphLaunch(g->step, s)); else enqueue_step(h, c);
       ++steps;
       h->launches += per_step;
+      if (ahead) {
+        WISB_CUDA(cudaMemcpyAsync(const_cast<int*>(flag) + (gs & 1), &h->st.p->all_done, sizeof(int), cudaMemcpyDeviceToHost, s));
+        WISB_CUDA(cudaEventRecord(h->ev_flag[gs & 1], s));
+        if (gs >= 1) {
+          WISB_CUDA(cudaEventSynchronize(h->ev_flag[(gs - 1) & 1]));
+          if (flag[(gs - 1) & 1]) {
+            --steps;  // the step just enqueued does nothing
+            break;
+          }
+        }
+        continue;
+      }
       const bool poll = ((gs + 1) % h->decode_poll == 0) || gs + 1 == c.max_new;
       if (poll) {
         WISB_CUDA(cudaMemcpyAsync(const_cast<int*>(flag), &h->st.p->all_done, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1145,7 +1166,7 @@ void enqueue_batch_step(wisb_handle* h, const DecodeCfg& c) {
   a.rows_per_utt = c.beam;
   a.with_logits = 1;
   a.done = h->done.p;
-  h->bd_launches_step = batch_pass_run(a, h->bd_layers.data(), h->dims.n_dec_layers, h->stream) + 4;
+  h->bd_launches_step = batch_pass_run(a, h->bd_layers.data(), h->dims.n_dec_layers, h->stream) + 2;
   search_step_run(make_batch_search_args(h, c), h->stream);
 }
 
@@ -1378,6 +1399,8 @@ int wisb_destroy(wisb_handle* h) {
     if (e) cudaEventDestroy(e);
   for (auto& e : h->prof_ev) cudaEventDestroy(e);
   if (h->own_blob && h->blob) cudaFree(h->blob);
+  for (cudaEvent_t ev : h->ev_flag)
+    if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;

@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(TK_THREADS) topk_partial_kernel(const SearchAr
   // the row's lse and into scores.  (This replaced a separate two-pass lse kernel: 55 us -> 0.)
   __shared__ unsigned long long s_red[32];
   __shared__ float s_f[32];
+  if (a.st->all_done) return;  // a step enqueued ahead of the host's poll
   const int chunk = blockIdx.x, r = blockIdx.y;
   const bool first = a.st->gen_step == 0;
   const float* row = a.logits + static_cast<long long>(r) * a.ldl;
@@ -126,10 +127,7 @@ __global__ void __launch_bounds__(TK_THREADS) topk_partial_kernel(const SearchAr
 // grid (n_utt): merge beam * TOPK_CHUNKS * n_cand partial keys -> sorted candidate list
 constexpr int TM_PER = (MAX_BEAM * TOPK_CHUNKS * MAX_CAND + TK_THREADS - 1) / TK_THREADS;  // 16
 
-__global__ void __launch_bounds__(TK_THREADS) topk_merge_kernel(const SearchArgs a) {
-  __shared__ unsigned long long s_red[32];
-  __shared__ unsigned long long s_out[MAX_CAND];
-  __shared__ float s_lse[MAX_BEAM];
+__device__ __forceinline__ void topk_merge_body(const SearchArgs& a, unsigned long long* s_red, unsigned long long* s_out, float* s_lse) {
   const int u = blockIdx.x;
   const int gen = a.st->gen_step;
   const bool first = gen == 0;
@@ -178,8 +176,8 @@ __global__ void __launch_bounds__(TK_THREADS) topk_merge_kernel(const SearchArgs
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// grid (n_utt), one warp: the CTranslate2 bookkeeping for one utterance
-__global__ void __launch_bounds__(32) search_bookkeeping_kernel(const SearchArgs a) {
+// one warp: the CTranslate2 bookkeeping for one utterance
+__device__ __forceinline__ void search_bookkeeping_body(const SearchArgs& a, int* s_pick, int& s_best_k, int& s_finished) {
   const int u = blockIdx.x, lane = threadIdx.x;
   const int beam = a.beam, V = a.n_vocab, nc = a.n_cand;
   const int gen = a.st->gen_step, pos = a.st->pos;
@@ -188,9 +186,6 @@ __global__ void __launch_bounds__(32) search_bookkeeping_kernel(const SearchArgs
   int* seq_nxt = a.seq[nxt_buf];
   const int* ind_cur = a.indir[cur];
   int* ind_nxt = a.indir[nxt_buf];
-  __shared__ int s_pick[MAX_BEAM];
-  __shared__ int s_best_k;
-  __shared__ int s_finished;
 
   if (a.done[u]) {
     // frozen utterance: carry the state over unchanged so the ping-pong buffers stay coherent
@@ -275,14 +270,38 @@ __global__ void __launch_bounds__(32) search_bookkeeping_kernel(const SearchArgs
   }
 }
 
-__global__ void search_advance_kernel(const SearchArgs a) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) {
-    a.st->pos += 1;
-    a.st->gen_step += 1;
-    *a.flip ^= 1;
+// grid (n_utt) x TK_THREADS: candidate merge, then (warp 0) the bookkeeping of the utterance, then -- by the last CTA to get
+// there -- the step advance (position, generation step, ping-pong flip, per-row positions).  One launch instead of three:
+// the tail of a decoding step is launch-latency bound.
+__global__ void __launch_bounds__(TK_THREADS) search_tail_kernel(const SearchArgs a) {
+  __shared__ unsigned long long s_red[32];
+  __shared__ unsigned long long s_out[MAX_CAND];
+  __shared__ float s_lse[MAX_BEAM];
+  __shared__ int s_pick[MAX_BEAM];
+  __shared__ int s_best_k;
+  __shared__ int s_finished;
+  __shared__ int s_last;
+  if (a.st->all_done) return;  // a step enqueued ahead of the host's poll: nothing left to do
+  topk_merge_body(a, s_red, s_out, s_lse);
+  __syncthreads();  // the candidate list (global) is complete for this CTA's readers
+  if (threadIdx.x < 32) search_bookkeeping_body(a, s_pick, s_best_k, s_finished);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int t = atomicAdd(&a.st->ticket, 1);
+    s_last = t == static_cast<int>(gridDim.x) - 1;
   }
-  if (a.row_pos != nullptr && i < a.n_utt * a.beam) a.row_pos[i] += 1;
+  __syncthreads();
+  if (s_last) {  // every utterance has read this step's position / generation step / flip
+    if (threadIdx.x == 0) {
+      a.st->ticket = 0;
+      a.st->pos += 1;
+      a.st->gen_step += 1;
+      *a.flip ^= 1;
+    }
+    if (a.row_pos != nullptr)
+      for (int i = threadIdx.x; i < a.n_utt * a.beam; i += blockDim.x) a.row_pos[i] += 1;
+  }
 }
 
 __global__ void prefill_rows_kernel(int* tokens, int* row_pos, int* row_slot, const int* prompt, int prompt_len, int rows,
@@ -313,6 +332,7 @@ __global__ void search_init_kernel(const SearchArgs a, const int* prompt, int sh
     a.st->gen_step = 0;
     a.st->n_done = 0;
     a.st->all_done = 0;
+    a.st->ticket = 0;
     *a.flip = 0;
   }
   for (int i = tid; i < R; i += n) {
@@ -362,9 +382,7 @@ void search_step_run(const SearchArgs& a, cudaStream_t stream) {
   WISB_REQUIRE(a.beam >= 1 && a.beam <= MAX_BEAM && a.n_cand <= MAX_CAND, "search: beam_size must be in [1, 8]");
   WISB_REQUIRE((a.n_vocab + TOPK_CHUNKS - 1) / TOPK_CHUNKS <= TK_THREADS * TK_PER, "search: vocabulary too large");
   topk_partial_kernel<<<dim3(TOPK_CHUNKS, R), TK_THREADS, 0, stream>>>(a);
-  topk_merge_kernel<<<a.n_utt, TK_THREADS, 0, stream>>>(a);
-  search_bookkeeping_kernel<<<a.n_utt, 32, 0, stream>>>(a);
-  search_advance_kernel<<<cdiv(R, 256), 256, 0, stream>>>(a);
+  search_tail_kernel<<<a.n_utt, TK_THREADS, 0, stream>>>(a);
   WISB_CUDA(cudaGetLastError());
 }
 
