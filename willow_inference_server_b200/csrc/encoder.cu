@@ -87,6 +87,8 @@ constexpr int LN_MAX_IT = 12;  // d <= 1536
 __global__ void __launch_bounds__(256)
 layernorm_f32_to_f16_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
                             __half* __restrict__ y, int rows, int d) {
+  pdl_launch_dependents();  // (programmatic dependent launch: the next kernel's prologue overlaps this one)
+  pdl_wait();               // the producer of x has completed
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -187,6 +189,8 @@ enc_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
+  pdl_launch_dependents();
+  pdl_wait();  // barriers, TMEM and descriptors were set up under the QKV GEMM's tail; its output is visible from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -390,10 +394,18 @@ void conv1_gelu_run(const float* mel, const __half* w, const float* bias, __half
 }
 
 void layernorm_f32_to_f16_run(const float* x, const float* g, const float* b, __half* y, int rows, int d,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, bool pdl) {
   WISB_REQUIRE(d % 128 == 0 && d <= 128 * LN_MAX_IT, "layernorm: d_model must be a multiple of 128, <= 1536");
-  layernorm_f32_to_f16_kernel<<<cdiv(rows, 8), 256, 0, stream>>>(x, g, b, y, rows, d);
-  WISB_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cdiv(rows, 8));
+  cfg.blockDim = dim3(256);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  WISB_CUDA(cudaLaunchKernelEx(&cfg, layernorm_f32_to_f16_kernel, x, g, b, y, rows, d));
 }
 
 void enc_attn_plan(AttnPlan& p, const __half* qkv, const __half* vt, __half* ctx, int B, int d, int H, bool v_mn_major) {
@@ -418,11 +430,20 @@ void enc_attn_run(const AttnPlan& p, cudaStream_t stream) {
     WISB_CUDA(cudaFuncSetAttribute(enc_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
   });
   dim3 grid(T_ENC_PAD / AT_BM, p.H, p.B);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(AT_THREADS);
+  cfg.dynamicSmemBytes = AT_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
   if (p.v_mn_major)
-    enc_attn_kernel<true><<<grid, AT_THREADS, AT_SMEM, stream>>>(p.map_q, p.map_k, p.map_v, p.ctx, p.d, p.H);
+    WISB_CUDA(cudaLaunchKernelEx(&cfg, enc_attn_kernel<true>, p.map_q, p.map_k, p.map_v, p.ctx, p.d, p.H));
   else
-    enc_attn_kernel<false><<<grid, AT_THREADS, AT_SMEM, stream>>>(p.map_q, p.map_k, p.map_v, p.ctx, p.d, p.H);
-  WISB_CUDA(cudaGetLastError());
+    WISB_CUDA(cudaLaunchKernelEx(&cfg, enc_attn_kernel<false>, p.map_q, p.map_k, p.map_v, p.ctx, p.d, p.H));
 }
 
 void enc_attn_ref_run(const __half* qkv, __half* ctx, int B, int d, int H, cudaStream_t stream) {

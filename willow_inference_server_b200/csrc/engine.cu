@@ -124,7 +124,7 @@ struct wisb_handle {
   CUtensorMap ckv_map;
   std::vector<EncLayerPlans> enc_plans;
   AttnPlan attn_plan;
-  int plans_B = 0, plans_vmn = -1;
+  int plans_B = 0, plans_vmn = -1, plans_pdl = -1;
   // decoder workspaces
   DevBuf<float> dx, dq, dctx, dh, logits;
   DevBuf<__half> dctx16, dh16, dxn16, dq16;
@@ -148,6 +148,7 @@ struct wisb_handle {
   GemmPlan bd_vocab;
   DevBuf<MegaLayer> mega_layers;
   DevBuf<__half> mega_img;  // warp-MMA pass: decoder weights as per-CTA shared-memory images (mega_mma_image)
+  int enc_pdl = 1;  // encoder: programmatic dependent launch along the whole kernel chain (227 launches per window)
   int mega_tc = 1, mega_dbg = 0;  // mega_dbg (timing experiments only): bit 0 every layer streams layer 0's weights and cross K/V (L2 resident), bit 1 a quarter of every weight unit
   DevBuf<unsigned> mega_flags;
   // optional reuse of the encoder output + cross K/V between consecutive calls on identical host features
@@ -490,7 +491,7 @@ void ensure_encoder(wisb_handle* h, int B) {
     make_tmap_f16_2d(&h->ckv_map, h->ckv.p, HEAD_DIM, static_cast<long long>(h->ckv.n / HEAD_DIM), HEAD_DIM, HEAD_DIM, 128);
     h->enc_cap = B;
   }
-  if (h->plans_B == B && h->plans_vmn == h->attn_v_mn) return;
+  if (h->plans_B == B && h->plans_vmn == h->attn_v_mn && h->plans_pdl == h->enc_pdl) return;
   const int Mi = static_cast<int>(M);
   {
     GemmEpi e;
@@ -545,6 +546,10 @@ void ensure_encoder(wisb_handle* h, int B) {
     gemm_plan(h->plan_ckv, h->enc_out.p, d, h->H("dec.crosskv.w"), Mi, dm.n_dec_layers * 2 * d, d, e, h->num_sms);
   }
   enc_attn_plan(h->attn_plan, h->qkv.p, h->vt.p, h->ctx.p, B, d, H, h->attn_v_mn != 0);
+  h->attn_plan.pdl = h->enc_pdl != 0;
+  h->plan_conv2.pdl = h->plan_ckv.pdl = h->enc_pdl;
+  for (EncLayerPlans& pl : h->enc_plans) pl.qkv.pdl = pl.o.pdl = pl.fc1.pdl = pl.fc2.pdl = h->enc_pdl;
+  h->plans_pdl = h->enc_pdl;
   h->plans_B = B;
   h->plans_vmn = h->attn_v_mn;
 }
@@ -568,7 +573,7 @@ void run_encoder(wisb_handle* h, int B, int n_layers, bool with_ckv, int mel_fir
     const std::string p = "enc." + std::to_string(i) + ".";
     EncLayerPlans& pl = h->enc_plans[i];
     h->prof_begin(2);
-    layernorm_f32_to_f16_run(h->x.p, h->F(p + "ln1.g"), h->F(p + "ln1.b"), h->xn.p, M, d, s);
+    layernorm_f32_to_f16_run(h->x.p, h->F(p + "ln1.g"), h->F(p + "ln1.b"), h->xn.p, M, d, s, h->enc_pdl != 0);
     h->prof_end();
     h->prof_begin(0);
     gemm_run(pl.qkv, s);
@@ -583,7 +588,7 @@ void run_encoder(wisb_handle* h, int B, int n_layers, bool with_ckv, int mel_fir
     gemm_run(pl.o, s);
     h->prof_end();
     h->prof_begin(2);
-    layernorm_f32_to_f16_run(h->x.p, h->F(p + "ln2.g"), h->F(p + "ln2.b"), h->xn.p, M, d, s);
+    layernorm_f32_to_f16_run(h->x.p, h->F(p + "ln2.g"), h->F(p + "ln2.b"), h->xn.p, M, d, s, h->enc_pdl != 0);
     h->prof_end();
     h->prof_begin(0);
     gemm_run(pl.fc1, s);
@@ -593,7 +598,7 @@ void run_encoder(wisb_handle* h, int B, int n_layers, bool with_ckv, int mel_fir
     h->prof_end();
   }
   h->prof_begin(2);
-  layernorm_f32_to_f16_run(h->x.p, h->F("enc.ln_post.g"), h->F("enc.ln_post.b"), h->enc_out.p, M, d, s);
+  layernorm_f32_to_f16_run(h->x.p, h->F("enc.ln_post.g"), h->F("enc.ln_post.b"), h->enc_out.p, M, d, s, h->enc_pdl != 0);
   h->prof_end();
   h->launches += 2 + 7 * nl + 1;
   if (with_ckv) {
@@ -1429,6 +1434,7 @@ int wisb_set_option(wisb_handle* h, const char* key, int value) {
     }
     else if (k == "mega_trace") h->mega_trace_on = value;
     else if (k == "mega_dbg") h->mega_dbg = value;
+    else if (k == "enc_pdl") h->enc_pdl = value ? 1 : 0;
     else if (k == "mega_trace_cta") h->mega_trace_cta = value;
     else if (k == "mega_trace_layer") h->mega_trace_layer = value;
     else if (k == "batch_rows") {

@@ -70,12 +70,13 @@ void conv1_gelu_run(const float* mel, const __half* w /*[d,240]*/, const float* 
                     cudaStream_t stream);
 // LayerNorm over rows of fp32 x [rows, d] -> fp16 y [rows, d]
 void layernorm_f32_to_f16_run(const float* x, const float* g, const float* b, __half* y, int rows, int d,
-                              cudaStream_t stream);
+                              cudaStream_t stream, bool pdl = false);
 // non-causal self-attention over the 1500 valid positions of each window; qkv [B*1536, 3d] fp16 -> ctx [B*1536, d] fp16
 struct AttnPlan {
   CUtensorMap map_q, map_k, map_v;
   int B = 0, d = 0, H = 0;
   bool v_mn_major = true;
+  bool pdl = false;  // programmatic dependent launch (the kernel's prologue overlaps its predecessor's tail)
   __half* ctx = nullptr;
 };
 void enc_attn_plan(AttnPlan& p, const __half* qkv, const __half* vt, __half* ctx, int B, int d, int H, bool v_mn_major);
