@@ -433,7 +433,7 @@ def run_ours(args):
     e2e_value = world * AUDIO_SECONDS * args.steps / wall_e2e
     dec_bytes = decoder_pass_bytes(dims, 1)
     steps_per = int(t["decode_steps"])  # decoder passes per utterance (prompt prefix in one pass + N_OUT search steps)
-    dec_traffic, dec_traffic_src = ncu_dram_traffic_per_launch("r02_dec_pass_kernel_full.csv", "r01_dec_pass_kernel_full.csv")
+    dec_traffic, dec_traffic_src = ncu_dram_traffic_per_launch("r02_dec_pass_mma_kernel_full.csv", "r02_dec_pass_kernel_full.csv", "r01_dec_pass_kernel_full.csv")
     gemm_traffic, gemm_traffic_src = ncu_dram_traffic_per_launch("r02_gemm_tc_full.csv", "r01_gemm_tc_full.csv")
     out = {
         "metric": "Whisper large-v2 realtime multiple (audio s / s), beam 5, 3.84 s utterance",
@@ -456,7 +456,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clocks,
         # dominant kernel of the step: the persistent decoder pass; HBM-bound weight streaming (bytes per pass: decoder_pass_bytes)
-        "roofline": {"bound": "hbm", "kernel": "dec_pass_kernel<5> (persistent decoder pass, one launch per generated token)",
+        "roofline": {"bound": "hbm", "kernel": "dec_pass_mma_kernel<5> (persistent decoder pass on the warp-level tensor path, one launch per generated token)",
                      "achieved": round(dec_bytes * steps_per / (stage["decode_ms"] / args.steps * 1e-3) / 1e9, 1),
                      "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None,
                      "traffic": dec_traffic,

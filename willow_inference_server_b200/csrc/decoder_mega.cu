@@ -179,7 +179,7 @@ __device__ __forceinline__ CrossGeom cross_geom(int n_utt, int H) {
   if (s < smin) s = smin;
   if (s > 16) s = 16;
   c.S = s;
-  c.KS = ((T_ENC + s - 1) / s + 15) & ~15;  // whole 16-key MMA blocks per split
+  c.KS = ((T_ENC + s - 1) / s + 31) & ~31;  // whole 32-key MMA blocks per split (7 splits: 224 keys = one block per warp)
   c.n_tasks = n_utt * H * s;
   return c;
 }
@@ -1069,8 +1069,36 @@ __device__ __forceinline__ void publish_resid(const MegaArgs& A, int r, int n, b
 template <int NMT>
 __device__ __forceinline__ void mma_unit(float (&acc)[4][4], uint32_t a_kb, uint32_t a_step, uint32_t b_kb, uint32_t b_step,
                                          int n_it, const uint32_t (&sw)[4]) {
+  // two k-blocks per trip into two accumulator sets: the second block's loads are in flight under the first block's
+  // HMMA chain (one warp per scheduler: a trip's latency chain is LDS -> ldmatrix -> 4 dependent HMMAs, ~135 ns measured)
+  float acc2[NMT][4];
+#pragma unroll
+  for (int m = 0; m < NMT; ++m)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc2[m][i] = 0.f;
+  int it = 0;
 #pragma unroll 1
-  for (int it = 0; it < n_it; ++it, a_kb += a_step, b_kb += b_step) {
+  for (; it + 1 < n_it; it += 2, a_kb += 2 * a_step, b_kb += 2 * b_step) {
+    const uint4 p01 = lds128(b_kb), p23 = lds128(b_kb + 16);
+    const uint4 q01 = lds128(b_kb + b_step), q23 = lds128(b_kb + b_step + 16);
+    const uint32_t bf[8] = {p01.x, p01.y, p01.z, p01.w, p23.x, p23.y, p23.z, p23.w};
+    const uint32_t bg[8] = {q01.x, q01.y, q01.z, q01.w, q23.x, q23.y, q23.z, q23.w};
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t af[NMT][4], ag[NMT][4];
+#pragma unroll
+      for (int m = 0; m < NMT; ++m) {
+        ldmatrix_x4(a_kb + sw[ks] + m * 2048, af[m]);
+        ldmatrix_x4(a_kb + a_step + sw[ks] + m * 2048, ag[m]);
+      }
+#pragma unroll
+      for (int m = 0; m < NMT; ++m) {
+        mma_m16n8k16(acc[m], af[m], bf[2 * ks], bf[2 * ks + 1]);
+        mma_m16n8k16(acc2[m], ag[m], bg[2 * ks], bg[2 * ks + 1]);
+      }
+    }
+  }
+  if (it < n_it) {
     const uint4 b01 = lds128(b_kb), b23 = lds128(b_kb + 16);  // {b0, b1} of k-steps 0, 1 | 2, 3 (fragment-major image)
     const uint32_t bf[8] = {b01.x, b01.y, b01.z, b01.w, b23.x, b23.y, b23.z, b23.w};
 #pragma unroll
@@ -1082,6 +1110,10 @@ __device__ __forceinline__ void mma_unit(float (&acc)[4][4], uint32_t a_kb, uint
       for (int m = 0; m < NMT; ++m) mma_m16n8k16(acc[m], af[m], bf[2 * ks], bf[2 * ks + 1]);
     }
   }
+#pragma unroll
+  for (int m = 0; m < NMT; ++m)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[m][i] += acc2[m][i];
 }
 
 // ------------------------------------------------------------------ warp-MMA pass: self-attention phase
@@ -1593,34 +1625,49 @@ __device__ __forceinline__ void consume_cross_fused(Ring& rg, const MegaArgs& A,
     mbar_wait(ring_full0 + 8u * stK, (unit / NS) & 1u);
     mbar_wait(ring_full0 + 8u * stV, ((unit + 1) / NS) & 1u);
     trace_ev(A, ctid, s_tr, 12);
-    const uint32_t lane_off = static_cast<uint32_t>(((lane & 7) + ((lane >> 3) & 1) * 8) * 128 + (lane >> 4) * 16);
-    const uint32_t sKl = ring_data0 + stK * MG_STAGE_BYTES + lane_off, sVl = ring_data0 + stV * MG_STAGE_BYTES + lane_off;
-    for (int blk = warp; blk * 16 < nk; blk += MG_CONS_WARPS) {
-      float sc[2][4];
+    // (the cross K/V rows arrive chunk-swizzled by the key index -- gemm_tc.cu EPI_CROSSKV kv_swizzle -- so ldmatrix is
+    //  conflict-free: lane's row inside a 16-key half, 16-byte chunk (2 kq + lane / 16) ^ (key & 7))
+    const uint32_t lane_row = static_cast<uint32_t>(((lane & 7) + ((lane >> 3) & 1) * 8) * 128);
+    const uint32_t lane_c = static_cast<uint32_t>(lane >> 4), lane_x = static_cast<uint32_t>(lane & 7);
+    const uint32_t sKl = ring_data0 + stK * MG_STAGE_BYTES + lane_row, sVl = ring_data0 + stV * MG_STAGE_BYTES + lane_row;
+    for (int blk = warp; blk * 32 < nk; blk += MG_CONS_WARPS) {  // 32 keys per trip: 4 score tiles of 8 keys
+      float sc[4][4];
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
+      for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int i = 0; i < 4; ++i) sc[nt][i] = 0.f;
-      // (K rows are 128 bytes apart, unswizzled: ldmatrix takes 8-way bank conflicts here, 32 cycles instead of 4 -- the
-      //  layout is shared with the tcgen05 cross-attention of the batched pass, which reads it through a TMA swizzle)
 #pragma unroll
       for (int kq = 0; kq < 4; ++kq) {
-        uint32_t kf[4];
-        ldmatrix_x4(sKl + blk * 2048 + kq * 32, kf);
         const uint32_t a4[4] = {aq[kq][0], 0u, aq[kq][1], 0u};
-        mma_m16n8k16(sc[0], a4, kf[0], kf[2]);
-        mma_m16n8k16(sc[1], a4, kf[1], kf[3]);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {  // keys 16 half .. 16 half + 15 of the block
+          uint32_t kf[4];
+          ldmatrix_x4(sKl + blk * 4096 + half * 2048 + (((2 * kq + lane_c) ^ lane_x) << 4), kf);
+          mma_m16n8k16(sc[2 * half], a4, kf[0], kf[2]);
+          mma_m16n8k16(sc[2 * half + 1], a4, kf[1], kf[3]);
+        }
       }
-      const int k0 = blk * 16 + 2 * tq;
-      float s0 = k0 < nk ? sc[0][0] : -INFINITY, s1 = k0 + 1 < nk ? sc[0][1] : -INFINITY;
-      float s2 = k0 + 8 < nk ? sc[1][0] : -INFINITY, s3 = k0 + 9 < nk ? sc[1][1] : -INFINITY;
-      float mx = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
+      // online softmax of row gq over the block's 32 keys (keys 8 nt + 2 tq, + 1 live in this lane)
+      float sv[8];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int k0 = blk * 32 + nt * 8 + 2 * tq;
+        sv[2 * nt] = k0 < nk ? sc[nt][0] : -INFINITY;
+        sv[2 * nt + 1] = k0 + 1 < nk ? sc[nt][1] : -INFINITY;
+      }
+      float mx = sv[0];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) mx = fmaxf(mx, sv[q]);
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
       const float mn = fmaxf(m_run, mx);
       const float al = __expf(m_run - mn);
-      const float p0 = __expf(s0 - mn), p1 = __expf(s1 - mn), p2 = __expf(s2 - mn), p3 = __expf(s3 - mn);
-      float rs = (p0 + p1) + (p2 + p3);
+      float pr[8], rs = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        pr[q] = __expf(sv[q] - mn);
+        rs += pr[q];
+      }
       rs += __shfl_xor_sync(0xffffffffu, rs, 1);
       rs += __shfl_xor_sync(0xffffffffu, rs, 2);
       l_run = fmaf(l_run, al, rs);
@@ -1630,14 +1677,17 @@ __device__ __forceinline__ void consume_cross_fused(Ring& rg, const MegaArgs& A,
         o[j][0] *= al;
         o[j][1] *= al;
       }
-      __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
-      const uint32_t pa[4] = {*reinterpret_cast<uint32_t*>(&h01), 0u, *reinterpret_cast<uint32_t*>(&h23), 0u};
 #pragma unroll
-      for (int jp = 0; jp < 4; ++jp) {
-        uint32_t vf[4];
-        ldmatrix_x4_trans(sVl + blk * 2048 + jp * 32, vf);
-        mma_m16n8k16(o[2 * jp], pa, vf[0], vf[1]);
-        mma_m16n8k16(o[2 * jp + 1], pa, vf[2], vf[3]);
+      for (int kk = 0; kk < 2; ++kk) {  // 16 keys per k-step
+        __half2 h01 = __floats2half2_rn(pr[4 * kk], pr[4 * kk + 1]), h23 = __floats2half2_rn(pr[4 * kk + 2], pr[4 * kk + 3]);
+        const uint32_t pa[4] = {*reinterpret_cast<uint32_t*>(&h01), 0u, *reinterpret_cast<uint32_t*>(&h23), 0u};
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
+          uint32_t vf[4];
+          ldmatrix_x4_trans(sVl + blk * 4096 + kk * 2048 + (((2 * jp + lane_c) ^ lane_x) << 4), vf);
+          mma_m16n8k16(o[2 * jp], pa, vf[0], vf[1]);
+          mma_m16n8k16(o[2 * jp + 1], pa, vf[2], vf[3]);
+        }
       }
     }
     trace_ev(A, ctid, s_tr, 13);

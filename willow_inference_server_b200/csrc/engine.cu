@@ -157,6 +157,7 @@ struct wisb_handle {
   std::vector<float> mel_cache;
   int mel_cache_B = 0;
   bool enc_valid = false;
+  int ckv_sw = 0, ckv_is_sw = 0;  // cross K/V layout wanted by the decoder pass of this call / layout of what is in HBM
   DevBuf<float> cross_part;
   DevBuf<unsigned> cross_flags;
   DevBuf<float> ln_fold;       // per LN-GEMV: s2[N] and folded bias[N] (qkv, cq, fc1 of every decoder layer, vocab)
@@ -554,6 +555,12 @@ void ensure_encoder(wisb_handle* h, int B) {
   h->plans_vmn = h->attn_v_mn;
 }
 
+// the persistent warp-MMA pass (<= 8 rows) reads the cross K/V rows chunk-swizzled (ldmatrix without bank conflicts); every
+// other decoder path reads them linear
+bool want_ckv_swizzle(const wisb_handle* h, int rows) {
+  return rows <= DEC_MAX_ROWS && h->decoder_batch != 2 && h->decoder_mega && h->mega_tc;
+}
+
 // mel (device, [B,80,3000]) -> enc_out fp16 [B*1536, d] (+ cross K/V when with_ckv)
 void run_encoder(wisb_handle* h, int B, int n_layers, bool with_ckv, int mel_first = 0) {
   const Dims& dm = h->dims;
@@ -604,7 +611,9 @@ void run_encoder(wisb_handle* h, int B, int n_layers, bool with_ckv, int mel_fir
   if (with_ckv) {
     WISB_CUDA(cudaEventRecord(h->ev[3], s));
     h->prof_begin(0);
+    h->plan_ckv.epi.kv_swizzle = h->ckv_sw;
     gemm_run(h->plan_ckv, s);
+    h->ckv_is_sw = h->ckv_sw;
     h->prof_end();
     h->launches += 1;
   }
@@ -1539,7 +1548,9 @@ int wisb_generate_ex(wisb_handle* h, const float* mel, int B, const int32_t* pro
     h->launches = 0;
     for (int i = 1; i <= 5; ++i) h->timing[i] = 0.f;
     WISB_CUDA(cudaEventRecord(h->ev[0], s));
-    const bool reuse = upload_mel(h, mel, B);
+    bool reuse = upload_mel(h, mel, B);
+    h->ckv_sw = want_ckv_swizzle(h, B * beam_size) ? 1 : 0;
+    if (reuse && h->ckv_is_sw != h->ckv_sw) reuse = false;  // cached cross K/V is in the other pass's layout (the features are still on the device)
     set_extra_suppress(h, extra_suppress, n_extra);
     WISB_CUDA(cudaEventRecord(h->ev[2], s));
     WISB_CUDA(cudaEventSynchronize(h->ev[2]));
@@ -1621,7 +1632,10 @@ int wisb_detect_language(wisb_handle* h, const float* mel, int B, int32_t* lang_
     WISB_REQUIRE(B >= 1 && B <= 4096, "B out of range");
     WISB_REQUIRE(lang_ids_out != nullptr && probs_out != nullptr, "output pointer is NULL");
     cudaStream_t s = h->stream;
-    encode_for_decode(h, B, upload_mel(h, mel, B));
+    bool reuse = upload_mel(h, mel, B);
+    h->ckv_sw = (h->decoder_mega && h->mega_tc) ? 1 : 0;  // language detection always runs the <= 8-row pass
+    if (reuse && h->ckv_is_sw != h->ckv_sw) reuse = false;
+    encode_for_decode(h, B, reuse);
     const int nl = dm.n_langs;
     h->lang_ids.ensure(nl);
     std::vector<int> ids(nl);
@@ -1741,6 +1755,7 @@ int wisb_debug_forced_logits(wisb_handle* h, const float* mel, const int32_t* to
     WISB_REQUIRE(h->blob != nullptr && tokens != nullptr && logits_out != nullptr && n_tokens >= 1 && n_tokens <= dm.n_text_ctx, "bad arguments");
     cudaStream_t s = h->stream;
     upload_mel(h, mel, 1);
+    h->ckv_sw = want_ckv_swizzle(h, 1) ? 1 : 0;
     run_encoder(h, 1, -1, true);
     DecodeCfg c;
     c.u0 = 0; c.n_utt = 1; c.B_total = 1; c.beam = 1; c.prompt_len = n_tokens; c.max_new = 1; c.max_hyp = 1; c.lp = 1.f;

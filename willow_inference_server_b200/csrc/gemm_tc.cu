@@ -113,8 +113,29 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, int row, int co
       const int c = within - kv * e.d_model;
       const int head = c >> 6, e0 = c & 63;
       const int b = row / T_ENC_PAD, t = row - b * T_ENC_PAD;
-      long long idx = ((((static_cast<long long>(layer) * 2 + kv) * e.batch + e.batch_off + b) * e.n_heads + head) * T_ENC_PAD + t) * 64 + e0;
-      store_f16x32(reinterpret_cast<__half*>(e.out) + idx, f);
+      long long idx = ((((static_cast<long long>(layer) * 2 + kv) * e.batch + e.batch_off + b) * e.n_heads + head) * T_ENC_PAD + t) * 64;
+      if (e.kv_swizzle) {
+        // persistent warp-MMA decoder pass: the 16-byte chunks of a key's 128-byte row are XOR-swizzled by the key index, so
+        // that the bulk-copied rows are ldmatrix-conflict-free in shared memory (unswizzled: 8-way conflicts, ~190 cycles
+        // per ldmatrix.x4 measured).  The batched pass reads the linear layout through a TMA swizzle instead.
+        uint4* row = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out) + idx);
+        const int c0 = e0 >> 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __half2 h0 = __floats2half2_rn(f[8 * i + 0], f[8 * i + 1]);
+          __half2 h1 = __floats2half2_rn(f[8 * i + 2], f[8 * i + 3]);
+          __half2 h2 = __floats2half2_rn(f[8 * i + 4], f[8 * i + 5]);
+          __half2 h3 = __floats2half2_rn(f[8 * i + 6], f[8 * i + 7]);
+          uint4 u;
+          u.x = *reinterpret_cast<uint32_t*>(&h0);
+          u.y = *reinterpret_cast<uint32_t*>(&h1);
+          u.z = *reinterpret_cast<uint32_t*>(&h2);
+          u.w = *reinterpret_cast<uint32_t*>(&h3);
+          row[(c0 + i) ^ (t & 7)] = u;
+        }
+      } else {
+        store_f16x32(reinterpret_cast<__half*>(e.out) + idx + e0, f);
+      }
       break;
     }
     case EPI_QKV_VT: {

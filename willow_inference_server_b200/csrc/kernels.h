@@ -30,6 +30,7 @@ struct GemmEpi {
   void* aux2 = nullptr;        // EPI_DEC_QKV: V cache of the layer
   int d_model = 0, n_heads = 0, batch = 0;  // EPI_CROSSKV / EPI_QKV_VT
   int batch_off = 0;           // EPI_CROSSKV: window b of this call is utterance batch_off + b of the `batch`-wide K/V buffer
+  int kv_swizzle = 0;          // EPI_CROSSKV: 16-byte chunks of a key row XOR-swizzled by the key index (warp-MMA decoder pass)
   const int* row_slot = nullptr;  // EPI_DEC_QKV: cache slot / position of every row (device arrays)
   const int* row_pos = nullptr;
   int t_cap = 0;               // EPI_DEC_QKV: positions per cache slot
