@@ -99,13 +99,16 @@ __device__ __forceinline__ int row_token(const MegaArgs& A, int r) {
 
 
 // fp16 activation exchange of the warp-MMA pass: element (row r, feature k) of a [K/64 k-blocks][R rows][64] buffer stored in
-// B-FRAGMENT order: inside a k-block, row r owns 4 slots of 32 bytes, slot t = (k / 2) % 4 holds the 8 words lane (g = r, t)
-// of mma.m16n8k16 feeds to the 4 k-steps {b0, b1} x 4 -- exactly the B-operand image a consumer CTA wants in shared memory.
+// B-FRAGMENT order: inside a k-block, lane slot (g = r, t = (k / 2) % 4) holds the 8 words that lane of mma.m16n8k16 feeds
+// to the 4 k-steps ({b0, b1} x 4), as two 16-byte planes -- exactly the B-operand image a consumer CTA wants in shared memory.
 // Its reload is ONE bulk copy (scripts/ubench_reload: 0.7 us against 1.4 us for the ld.global reload of the same 25.6 KB)
 // and a lane fetches a whole k-block's fragments with two 16-byte loads.
 __device__ __forceinline__ long long act16_off(int R, int r, int k) {
+  // k-block: [plane p = k-steps {0,1} | {2,3}][lane slot r * 4 + t][4 words]: a warp's 16-byte fragment load touches 512
+  // consecutive bytes (32-byte strides gave 2-way bank conflicts)
   const int kk = k & 63;
-  return static_cast<long long>(k >> 6) * (R * 64) + (r * 4 + ((kk >> 1) & 3)) * 16 + ((kk >> 4) * 2 + ((kk >> 3) & 1)) * 2 + (kk & 1);
+  const int w = (kk >> 4) * 2 + ((kk >> 3) & 1);  // word of the lane's 8: k-step * 2 + {b0, b1}
+  return static_cast<long long>(k >> 6) * (R * 64) + (w >> 2) * (R * 32) + (r * 4 + ((kk >> 1) & 3)) * 8 + (w & 3) * 2 + (kk & 1);
 }
 // attention output of row r, features [col, col + 2): fp32 [R, d] (SIMT pass) or the fp16 exchange image (warp-MMA pass)
 __device__ __forceinline__ void store_ctx2(const MegaArgs& A, int r, int col, float v0, float v1) {
@@ -1068,7 +1071,7 @@ __device__ __forceinline__ void publish_resid(const MegaArgs& A, int r, int n, b
 // the lane's row swizzle folded in), sw[ks]: the lane's swizzled 16-byte chunk of k-step ks.
 template <int NMT>
 __device__ __forceinline__ void mma_unit(float (&acc)[4][4], uint32_t a_kb, uint32_t a_step, uint32_t b_kb, uint32_t b_step,
-                                         int n_it, const uint32_t (&sw)[4]) {
+                                         int n_it, const uint32_t (&sw)[4], uint32_t b_plane) {
   // two k-blocks per trip into two accumulator sets: the second block's loads are in flight under the first block's
   // HMMA chain (one warp per scheduler: a trip's latency chain is LDS -> ldmatrix -> 4 dependent HMMAs, ~135 ns measured)
   float acc2[NMT][4];
@@ -1079,8 +1082,8 @@ __device__ __forceinline__ void mma_unit(float (&acc)[4][4], uint32_t a_kb, uint
   int it = 0;
 #pragma unroll 1
   for (; it + 1 < n_it; it += 2, a_kb += 2 * a_step, b_kb += 2 * b_step) {
-    const uint4 p01 = lds128(b_kb), p23 = lds128(b_kb + 16);
-    const uint4 q01 = lds128(b_kb + b_step), q23 = lds128(b_kb + b_step + 16);
+    const uint4 p01 = lds128(b_kb), p23 = lds128(b_kb + b_plane);
+    const uint4 q01 = lds128(b_kb + b_step), q23 = lds128(b_kb + b_step + b_plane);
     const uint32_t bf[8] = {p01.x, p01.y, p01.z, p01.w, p23.x, p23.y, p23.z, p23.w};
     const uint32_t bg[8] = {q01.x, q01.y, q01.z, q01.w, q23.x, q23.y, q23.z, q23.w};
 #pragma unroll
@@ -1099,7 +1102,7 @@ __device__ __forceinline__ void mma_unit(float (&acc)[4][4], uint32_t a_kb, uint
     }
   }
   if (it < n_it) {
-    const uint4 b01 = lds128(b_kb), b23 = lds128(b_kb + 16);  // {b0, b1} of k-steps 0, 1 | 2, 3 (fragment-major image)
+    const uint4 b01 = lds128(b_kb), b23 = lds128(b_kb + b_plane);  // {b0, b1} of k-steps 0, 1 | 2, 3 (fragment-major image)
     const uint32_t bf[8] = {b01.x, b01.y, b01.z, b01.w, b23.x, b23.y, b23.z, b23.w};
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
@@ -1342,7 +1345,7 @@ __device__ __forceinline__ void consume_gemv_mma(Ring& rg, const MegaArgs& A, co
   prefetch_epi(0, first_rows);
   const int gq = lane >> 2, tq = lane & 3;
   const int brow = gq < R ? gq : R - 1;  // lanes whose activation row does not exist read the last row: their output columns are never stored
-  const uint32_t b_lane = smem_u32(s_b) + (brow * 4 + tq) * 32;
+  const uint32_t b_lane = smem_u32(s_b) + (brow * 4 + tq) * 16, b_plane = static_cast<uint32_t>(R * 64);
   const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;
   uint32_t sw[4];
 #pragma unroll
@@ -1377,10 +1380,10 @@ __device__ __forceinline__ void consume_gemv_mma(Ring& rg, const MegaArgs& A, co
       const uint32_t b_kb = b_lane + kb_next * R * 128;
       const uint32_t a_step = MG_CONS_WARPS * rows * 128, b_step = MG_CONS_WARPS * R * 128;
       switch (n_mt) {
-        case 1: mma_unit<1>(acc, a_kb, a_step, b_kb, b_step, n_it, sw); break;
-        case 2: mma_unit<2>(acc, a_kb, a_step, b_kb, b_step, n_it, sw); break;
-        case 3: mma_unit<3>(acc, a_kb, a_step, b_kb, b_step, n_it, sw); break;
-        default: mma_unit<4>(acc, a_kb, a_step, b_kb, b_step, n_it, sw); break;
+        case 1: mma_unit<1>(acc, a_kb, a_step, b_kb, b_step, n_it, sw, b_plane); break;
+        case 2: mma_unit<2>(acc, a_kb, a_step, b_kb, b_step, n_it, sw, b_plane); break;
+        case 3: mma_unit<3>(acc, a_kb, a_step, b_kb, b_step, n_it, sw, b_plane); break;
+        default: mma_unit<4>(acc, a_kb, a_step, b_kb, b_step, n_it, sw, b_plane); break;
       }
       kb_next += n_it * MG_CONS_WARPS;
       __syncwarp();
@@ -1536,7 +1539,7 @@ __device__ __forceinline__ void consume_cross_fused(Ring& rg, const MegaArgs& A,
     if (l == 0) s_lnstat[q] = t;
   }
   const int brow = gq < R ? gq : R - 1;
-  const uint32_t b_lane = smem_u32(s_b) + FUSED_B_OFF + (brow * 4 + tq) * 32;
+  const uint32_t b_lane = smem_u32(s_b) + FUSED_B_OFF + (brow * 4 + tq) * 16, b_plane = static_cast<uint32_t>(R * 64);
   const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;
   uint32_t sw[4];
 #pragma unroll
@@ -1571,7 +1574,7 @@ __device__ __forceinline__ void consume_cross_fused(Ring& rg, const MegaArgs& A,
       const int kbi = kb_next - kb0;
       const int n_it = kbi < nkb ? (nkb - kbi + MG_CONS_WARPS - 1) / MG_CONS_WARPS : 0;
       mma_unit<4>(acc, a_lane + st * MG_STAGE_BYTES + kbi * 64 * 128, MG_CONS_WARPS * 64 * 128, b_lane + kb_next * R * 128,
-                  MG_CONS_WARPS * R * 128, n_it, sw);
+                  MG_CONS_WARPS * R * 128, n_it, sw, b_plane);
       kb_next += n_it * MG_CONS_WARPS;
       __syncwarp();
       if (lane == 0) mbar_arrive(ring_empty0 + 8u * st);
@@ -1597,7 +1600,7 @@ __device__ __forceinline__ void consume_cross_fused(Ring& rg, const MegaArgs& A,
         const float mean = s_lnstat[2 * r] / d;
         const float rstd = rsqrtf(fmaxf(s_lnstat[2 * r + 1] / d - mean * mean, 0.f) + 1e-5f);
         v = rstd * (v - mean * e_s2[j]) + e_bias[j];
-        reinterpret_cast<__half*>(s_q)[rl * 64 + c] = __float2half_rn(v * 0.125f);  // pre-scaled query
+        reinterpret_cast<__half*>(s_q)[rl * 72 + c] = __float2half_rn(v * 0.125f);  // pre-scaled query; 144-byte rows: conflict-free fragment loads
       }
     }
     cons_sync();
@@ -1609,7 +1612,7 @@ __device__ __forceinline__ void consume_cross_fused(Ring& rg, const MegaArgs& A,
     uint32_t aq[4][2];
     {
       const bool row_ok = gq < beam;
-      const uint32_t qa = smem_u32(s_q) + (row_ok ? gq : 0) * 128 + tq * 4;
+      const uint32_t qa = smem_u32(s_q) + (row_ok ? gq : 0) * 144 + tq * 4;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         aq[ks][0] = row_ok ? lds32(qa + ks * 32) : 0u;
