@@ -60,6 +60,26 @@ def test_mixed_duration_batch_properties(large):
     assert len(langs) == 2 and abs(sum(p for _, p in langs[0]) - 1.0) < 1e-3
 
 
+def test_small_path_batches_equal_solo_runs_at_full_size(large):
+    # large-v2, <= 8 rows in one persistent pass: with 20 heads and several utterances the fused cross-attention phase gives
+    # most CTAs more than one (utterance, head, key split) task -- every utterance must still decode exactly as it does alone
+    dims, h = large
+    mel = audio.log_mel_batch([_synth(61440, 1), _synth(160000, 2), _synth(100000, 5), _synth(61440, 7), _synth(30000, 9)], h)
+    P = np.array([PROMPT], np.int32)
+    for n_utt, beam in ((5, 1), (2, 3), (4, 2)):
+        ids, _ = h.generate(mel[:n_utt], np.repeat(P, n_utt, 0), beam, max_length=20)
+        solo = [h.generate(mel[i : i + 1], P, beam, max_length=20)[0][0] for i in range(n_utt)]
+        assert ids == solo, (n_utt, beam)
+        assert all(0 < len(s) <= 10 for s in ids)
+    h.set_option("mega_mma", 0)  # the SIMT pass agrees on greedy decoding of the same batch
+    try:
+        simt, _ = h.generate(mel[:5], np.repeat(P, 5, 0), 1, max_length=20)
+    finally:
+        h.set_option("mega_mma", 1)
+    mma, _ = h.generate(mel[:5], np.repeat(P, 5, 0), 1, max_length=20)
+    assert sum(a == b for a, b in zip(simt, mma)) >= 4  # (fp16 vs fp32 activations: a near-tie may flip one transcript)
+
+
 def test_handles_coexist_and_threads(large):
     dims, h = large
     small_dims = W.WhisperDims(d_model=128, n_heads=2, n_enc_layers=2, n_dec_layers=2)

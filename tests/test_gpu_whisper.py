@@ -119,6 +119,25 @@ def test_persistent_pass_kernel_vs_per_op_chain(pair):
         assert ids_a[i] == ids_s[i] == res[i].sequences_ids[0], i
 
 
+@pytest.mark.parametrize("n_utt,beam", [(2, 3), (4, 2), (8, 1), (3, 2)])
+def test_small_path_several_utterances_per_pass(pair, n_utt, beam):
+    # <= 8 rows: several utterances x beams inside ONE persistent pass (the warp-MMA pass and the SIMT pass alike): every
+    # utterance decodes exactly as it does alone, and as the oracle says on its robust cases
+    dims, oracle, h = pair
+    mel = mel_inputs(8)[:n_utt]
+    res, robust = robust_cases(oracle, mel, [PROMPT] * n_utt, beam)
+    for mma in (1, 0):
+        h.set_option("mega_mma", mma)
+        try:
+            ids, _ = h.generate(mel, [PROMPT] * n_utt, beam_size=beam)
+            solo = [h.generate(mel[i : i + 1], [PROMPT], beam_size=beam)[0][0] for i in range(n_utt)]
+        finally:
+            h.set_option("mega_mma", 1)
+        assert ids == solo, (mma, n_utt, beam)
+        for i in robust:
+            assert ids[i] == res[i].sequences_ids[0], (mma, n_utt, beam, i)
+
+
 def test_max_length_and_suppress(pair):
     dims, oracle, h = pair
     mel = mel_inputs(4)[:1]

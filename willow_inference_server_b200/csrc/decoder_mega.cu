@@ -969,11 +969,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) dec_pass_kernel(const MegaArgs 
 // =====================================================================================================================
 // shared-memory plan of the warp-MMA kernel: ring | B operand (aliased by the attention scratch) | partial tiles | barriers,
 // statistics, trace cursor, owned residual columns | cache-slot tables | layer descriptors | phase geometry
+constexpr int FUSED_B_OFF = 36864;  // fused cross phase: its B operand image inside s_b, above the merge area and the statistic shares
 template <int NR>
 struct MmaSmem {
   static constexpr int NS = NR <= 5 ? 4 : 3;                 // ring stages: a whole next phase's weights fit ahead of the consumers
   static constexpr int B_BYTES = (5120 / 64) * NR * 128;     // B operand image of the largest K (fc2): [K/64][R][128 B]
-  static constexpr int B_MIN = 32768 + 20 * NR * 128;        // fused cross phase: merge area | statistics | B operand at 32 KB
+  static constexpr int B_MIN = FUSED_B_OFF + 20 * NR * 128;  // fused cross phase: merge area | statistics | B operand
   static constexpr int B_ALLOC = B_BYTES > B_MIN ? (B_BYTES > MG_SCRATCH ? B_BYTES : MG_SCRATCH) : (B_MIN > MG_SCRATCH ? B_MIN : MG_SCRATCH);
   static constexpr int OFF_B = NS * MG_STAGE_BYTES;          // (an m-tile's 16-row read may run 1 KB past its box: harmless)
   static constexpr int OFF_PART = OFF_B + B_ALLOC;
@@ -986,7 +987,8 @@ struct MmaSmem {
   static constexpr int TOTAL = OFF_GEOM + 5 * 64;
   static constexpr int STAT_OFF = 24576;                     // row-statistics shares land behind the image of a K <= 1280 phase
   static_assert(TOTAL <= 232448, "warp-MMA decoder pass: shared memory");
-  static_assert(20 * NR * 128 <= STAT_OFF && STAT_OFF + 160 * NR * 8 <= B_ALLOC, "statistics landing zone");
+  static_assert(20 * NR * 128 <= STAT_OFF && STAT_OFF + 160 * NR * 8 <= FUSED_B_OFF && FUSED_B_OFF + 20 * NR * 128 <= B_ALLOC,
+                "statistics landing zone / fused-phase B operand");
 };
 constexpr int MM_GROUP_ROWS = 64;       // weight rows per accumulation group (4 m-tiles)
 constexpr int MM_PART_LD = 68;          // partial tiles [warp][8 rows][68]: conflict-free fragment stores
@@ -1397,14 +1399,17 @@ __device__ __forceinline__ void consume_gemv_mma(Ring& rg, const MegaArgs& A, co
     trace_ev(A, ctid, s_tr, 4);
     // ---- row statistics (first group only): quantity q = (row, sum | sum of squares) is added up over the G per-CTA
     //      shares by 16 lanes, in a fixed order
-    if (gi == 0 && ln && ctid < 2 * R * 16) {
-      const int q = ctid >> 4, l = ctid & 15;
+    if (gi == 0 && ln) {
       const float* stp = reinterpret_cast<const float*>(s_b + SM::STAT_OFF);
-      float t = 0.f;
-      for (int i = l; i < G; i += 16) t += stp[i * 2 * R + q];
+      const int l = ctid & 15;
+      const unsigned hmask = 0xFFFFu << (ctid & 16);  // the two 16-lane groups of a warp may run different trip counts
+      for (int q = ctid >> 4; q < 2 * R; q += MG_CONS / 16) {  // (8 rows: 16 quantities, 14 lane groups)
+        float t = 0.f;
+        for (int i = l; i < G; i += 16) t += stp[i * 2 * R + q];
 #pragma unroll
-      for (int off = 8; off >= 1; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-      if (l == 0) s_lnstat[q] = t;
+        for (int off = 8; off >= 1; off >>= 1) t += __shfl_xor_sync(hmask, t, off);
+        if (l == 0) s_lnstat[q] = t;
+      }
     }
     // ---- the warps' partial tiles -> shared memory [warp][activation row][weight row], summed by the epilogue threads
 #pragma unroll
@@ -1480,7 +1485,6 @@ __device__ __forceinline__ void consume_gemv_mma(Ring& rg, const MegaArgs& A, co
 // itself (all R rows: 64 x 1280 weights = 164 KB per CTA through the ring, the same bytes for the 7 splits of a head, so HBM
 // still reads W once and the L2 serves the rest), then walks its keys as before.  Weight image: mega_mma_image with one
 // "owner" per head.  B operand (the LayerNorm-scaled residual rows) and statistic shares: reloaded by the barrier's opener.
-constexpr int FUSED_B_OFF = 32768;  // B operand image of the fused phase inside s_b (the merge area below it stays free)
 template <int NS>
 __device__ __forceinline__ void produce_cross_fused(Ring& rg, const MegaArgs& A, const MegaLayer& ly, const MmaGeom* s_geom) {
   const CrossGeom cg = cross_geom(A.n_utt, A.H);
@@ -1529,14 +1533,17 @@ __device__ __forceinline__ void consume_cross_fused(Ring& rg, const MegaArgs& A,
   // the LayerNorm-scaled residual rows + statistic shares (issued by the thread that saw the barrier open)
   mbar_wait(xbar, x_count & 1u);
   ++x_count;
-  if (ctid < 2 * R * 16) {  // row statistics, as in consume_gemv_mma
-    const int q = ctid >> 4, l = ctid & 15;
+  {  // row statistics, as in consume_gemv_mma
     const float* stp = reinterpret_cast<const float*>(s_b + stat_off);
-    float t = 0.f;
-    for (int i = l; i < G; i += 16) t += stp[i * 2 * R + q];
+    const int l = ctid & 15;
+    const unsigned hmask = 0xFFFFu << (ctid & 16);
+    for (int q = ctid >> 4; q < 2 * R; q += MG_CONS / 16) {
+      float t = 0.f;
+      for (int i = l; i < G; i += 16) t += stp[i * 2 * R + q];
 #pragma unroll
-    for (int off = 8; off >= 1; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-    if (l == 0) s_lnstat[q] = t;
+      for (int off = 8; off >= 1; off >>= 1) t += __shfl_xor_sync(hmask, t, off);
+      if (l == 0) s_lnstat[q] = t;
+    }
   }
   const int brow = gq < R ? gq : R - 1;
   const uint32_t b_lane = smem_u32(s_b) + FUSED_B_OFF + (brow * 4 + tq) * 16, b_plane = static_cast<uint32_t>(R * 64);
