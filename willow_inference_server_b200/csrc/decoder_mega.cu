@@ -1965,26 +1965,20 @@ void dec_pass_run(const MegaArgs& a, int num_sms, cudaStream_t stream) {
   WISB_REQUIRE(a.d % 64 == 0 && a.d <= MG_KC_MAX, "decoder pass: d_model <= 1536");
   WISB_REQUIRE((a.d + num_sms - 1) / num_sms <= 16, "decoder pass: too few SMs for the per-CTA residual slice");
   WISB_REQUIRE(num_sms <= 160, "decoder pass: more SMs than barrier flags");
-  static bool attr_done[64] = {};  // per device: function attributes belong to the device's context
-  int dev = 0;
-  WISB_CUDA(cudaGetDevice(&dev));
-  bool& attr_set = attr_done[dev & 63];
-  if (!attr_set) {
+  static std::atomic<unsigned long long> once{0};  // per device: function attributes belong to the device's context
+  once_per_device(once, [] {
     WISB_CUDA(cudaFuncSetAttribute(dec_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
     WISB_CUDA(cudaFuncSetAttribute(dec_pass_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
     WISB_CUDA(cudaFuncSetAttribute(dec_pass_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM));
-    attr_set = true;
-  }
+  });
   void* args[] = {const_cast<MegaArgs*>(&a)};
   if (a.tc) {
-    static bool tc_attr_done[64] = {};
-    bool& tc_set = tc_attr_done[dev & 63];
-    if (!tc_set) {
+    static std::atomic<unsigned long long> once_mma{0};
+    once_per_device(once_mma, [] {
       WISB_CUDA(cudaFuncSetAttribute(dec_pass_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem<2>::TOTAL));
       WISB_CUDA(cudaFuncSetAttribute(dec_pass_mma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem<5>::TOTAL));
       WISB_CUDA(cudaFuncSetAttribute(dec_pass_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, MmaSmem<8>::TOTAL));
-      tc_set = true;
-    }
+    });
     WISB_REQUIRE(a.d % 64 == 0 && 4 * a.d <= 5120, "warp-MMA decoder pass: d_model <= 1280");
     WISB_REQUIRE((a.d + num_sms - 1) / num_sms <= 16, "warp-MMA decoder pass: too few SMs for the per-CTA residual slice");
     if (a.R <= 2) {
