@@ -1,4 +1,4 @@
-"""Tensor-core persistent pass vs SIMT persistent pass: teacher-forced logit error against the oracle (tiny model), then
+"""Warp-MMA persistent pass (option mega_mma = 1, the default) vs SIMT persistent pass: teacher-forced logit error against the oracle (tiny model), then
 the large-v2 headline step timed with both."""
 import os
 import sys

@@ -15,7 +15,7 @@ GROUPS = collections.OrderedDict([
     ("tcgen05_mma(UTC*MMA)", re.compile(r"\bUTC[A-Z]*MMA")), ("tcgen05_ld_st(LDTM/STTM)", re.compile(r"\b(LDTM|STTM)")),
     ("tma_tensor(UTMALDG/UTMASTG)", re.compile(r"\b(UTMALDG|UTMASTG)")), ("tma_bulk(UBLKCP)", re.compile(r"\bUBLKCP")),
     ("mbarrier(SYNCS)", re.compile(r"\bSYNCS")), ("cp_async(LDGSTS)", re.compile(r"\bLDGSTS")),
-    ("legacy_mma(HMMA)", re.compile(r"\bHMMA")), ("fp32_fma(FFMA)", re.compile(r"\bFFMA")),
+    ("warp_mma(HMMA)", re.compile(r"\bHMMA")), ("ldmatrix(LDSM)", re.compile(r"\bLDSM")), ("fp32_fma(FFMA)", re.compile(r"\bFFMA")),
 ])
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
 name, counts, total = None, collections.OrderedDict(), collections.Counter()
